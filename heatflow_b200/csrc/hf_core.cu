@@ -1,0 +1,763 @@
+// heatflow_b200 - context, mesh/dof-map/sparsity, P1 assembly, time step, C-ABI (sm_100a).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "hf_ctx.cuh"
+
+int hf_pcg_prepare(hf_ctx* c);
+int hf_pcg_prepare_from_r(hf_ctx* c);
+
+thread_local std::string hf_err_msg;
+int hf_fail(int code, const std::string& msg) {
+  hf_err_msg = msg;
+  return code;
+}
+
+extern "C" int hf_version(void) { return 100; }
+extern "C" const char* hf_last_error(void) { return hf_err_msg.c_str(); }
+extern "C" int hf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" hf_ctx* hf_create(int device) {
+  int n = hf_device_count();
+  if (n <= 0) {
+    hf_fail(HF_ERR_CUDA, "hf_create: no CUDA device available (there is no CPU fallback)");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    hf_fail(HF_ERR_ARG, "hf_create: device index out of range");
+    return nullptr;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    hf_fail(HF_ERR_CUDA, "hf_create: cudaSetDevice failed");
+    return nullptr;
+  }
+  hf_ctx* c = new hf_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    hf_fail(HF_ERR_CUDA, "hf_create: cudaStreamCreate failed");
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" void hf_destroy(hf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  hf_ens_free(c);
+  if (c->ws.h_ctrl) cudaFreeHost(c->ws.h_ctrl);
+  c->opA.drop_graphs();
+  c->opMr.drop_graphs();
+  cudaStream_t s = c->stream;
+  delete c;
+  cudaStreamDestroy(s);
+}
+
+// ---------------------------------------------------------------------------------------
+// mesh -> dof map, node->cell adjacency, CSR sparsity pattern (host, integer work, one-off)
+// ---------------------------------------------------------------------------------------
+extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const double* xy,
+                           const int32_t* cells, const int32_t* cell_tag) {
+  if (!c || !xy || !cells || !cell_tag) return hf_fail(HF_ERR_ARG, "hf_set_mesh: null argument");
+  if (N <= 0 || E <= 0 || (nv != 2 && nv != 3)) return hf_fail(HF_ERR_ARG, "hf_set_mesh: need N > 0, E > 0, nv in {2,3}");
+  for (int64_t k = 0; k < (int64_t)E * nv; ++k)
+    if (cells[k] < 0 || cells[k] >= N) return hf_fail(HF_ERR_ARG, "hf_set_mesh: cell references a node outside [0, N)");
+  cudaSetDevice(c->device);
+  c->N = N;
+  c->E = E;
+  c->nv = nv;
+  c->Npad = (N + HF_SLICE - 1) / HF_SLICE * HF_SLICE;
+  c->op_built = c->proj_built = false;
+  // node -> cells, ascending cell index (fixes the summation order of the gather assembly)
+  std::vector<int> ptr(N + 1, 0);
+  for (int64_t k = 0; k < (int64_t)E * nv; ++k) ptr[cells[k] + 1]++;
+  for (int i = 0; i < N; ++i) ptr[i + 1] += ptr[i];
+  std::vector<int> idx((size_t)E * nv), fill(ptr.begin(), ptr.end() - 1);
+  for (int e = 0; e < E; ++e)
+    for (int a = 0; a < nv; ++a) idx[fill[cells[(size_t)e * nv + a]]++] = e;
+  // pattern: neighbours through shared cells, plus the diagonal, sorted
+  c->h_rowptr.assign(N + 1, 0);
+  c->h_col.clear();
+  c->h_col.reserve((size_t)N * 8);
+  std::vector<int> tmp;
+  for (int i = 0; i < N; ++i) {
+    tmp.clear();
+    for (int a = ptr[i]; a < ptr[i + 1]; ++a)
+      for (int b = 0; b < nv; ++b) tmp.push_back(cells[(size_t)idx[a] * nv + b]);
+    std::sort(tmp.begin(), tmp.end());
+    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    c->h_col.insert(c->h_col.end(), tmp.begin(), tmp.end());
+    if (c->h_col.size() > (size_t)INT32_MAX) return hf_fail(HF_ERR_ARG, "hf_set_mesh: nnz exceeds int32");
+    c->h_rowptr[i + 1] = (int)c->h_col.size();
+  }
+  c->nnz = (int64_t)c->h_col.size();
+  HF_TRY(c->xy.upload(xy, (size_t)N * 2, c->stream));
+  HF_TRY(c->cells.upload(cells, (size_t)E * nv, c->stream));
+  HF_TRY(c->cell_tag.upload(cell_tag, E, c->stream));
+  HF_TRY(c->n2c_ptr.upload(ptr.data(), N + 1, c->stream));
+  HF_TRY(c->n2c_idx.upload(idx.data(), idx.size(), c->stream));
+  HF_TRY(c->rowptr.upload(c->h_rowptr.data(), N + 1, c->stream));
+  HF_TRY(c->col.upload(c->h_col.data(), c->h_col.size(), c->stream));
+  HF_TRY(c->cm.alloc(E, c->stream));
+  HF_TRY(c->ck.alloc(E, c->stream));
+  HF_TRY(c->bcflag.alloc(c->Npad, c->stream));
+  HF_TRY(c->gfull.alloc(c->Npad, c->stream));
+  HF_TRY(c->u.alloc(c->Npad, c->stream));
+  HF_TRY(c->uprev.alloc(c->Npad, c->stream));
+  HF_TRY(c->b.alloc(c->Npad, c->stream));
+  HF_TRY(c->source.alloc(c->Npad, c->stream));
+  c->have_prev = c->have_source = false;
+  c->n_bc = c->n_gauss = 0;
+  HF_TRY(hf_pcg_alloc(c));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return HF_OK;
+}
+
+extern "C" int hf_set_materials(hf_ctx* c, int32_t n, const int32_t* tags, const double* kappa, const double* rho_c) {
+  if (!c || n <= 0 || !tags || !kappa || !rho_c) return hf_fail(HF_ERR_ARG, "hf_set_materials: bad arguments");
+  c->mat_tags.assign(tags, tags + n);
+  c->mat_kappa.assign(kappa, kappa + n);
+  c->mat_rhoc.assign(rho_c, rho_c + n);
+  c->op_built = false;
+  return HF_OK;
+}
+
+__global__ void k_scatter_bc(int n, const int* __restrict__ dofs, const double* __restrict__ val,
+                             unsigned char* __restrict__ flag, double* __restrict__ g) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    if (flag) flag[dofs[i]] = 1;
+    g[dofs[i]] = val[i];
+  }
+}
+
+extern "C" int hf_set_bcs(hf_ctx* c, int32_t n_bc, const int32_t* bc_dofs, const double* bc_value,
+                          int32_t n_gauss, const int32_t* gauss_slot, const double* gauss_r) {
+  if (!c || c->N == 0) return hf_fail(HF_ERR_STATE, "hf_set_bcs: call hf_set_mesh first");
+  if (n_bc < 0 || n_gauss < 0 || (n_bc && (!bc_dofs || !bc_value)) || (n_gauss && (!gauss_slot || !gauss_r)))
+    return hf_fail(HF_ERR_ARG, "hf_set_bcs: bad arguments");
+  for (int i = 0; i < n_bc; ++i) {
+    if (bc_dofs[i] < 0 || bc_dofs[i] >= c->N) return hf_fail(HF_ERR_ARG, "hf_set_bcs: dof out of range");
+    if (i && bc_dofs[i] <= bc_dofs[i - 1]) return hf_fail(HF_ERR_ARG, "hf_set_bcs: bc_dofs must be sorted and unique");
+  }
+  std::vector<int> gd(n_gauss);
+  for (int i = 0; i < n_gauss; ++i) {
+    if (gauss_slot[i] < 0 || gauss_slot[i] >= n_bc) return hf_fail(HF_ERR_ARG, "hf_set_bcs: gauss_slot out of range");
+    gd[i] = bc_dofs[gauss_slot[i]];
+  }
+  cudaSetDevice(c->device);
+  c->n_bc = n_bc;
+  c->n_gauss = n_gauss;
+  HF_CUDA(cudaMemsetAsync(c->bcflag.p, 0, c->Npad, c->stream));
+  HF_CUDA(cudaMemsetAsync(c->gfull.p, 0, sizeof(double) * c->Npad, c->stream));
+  HF_TRY(c->bc_dofs.upload(bc_dofs, n_bc, c->stream));
+  HF_TRY(c->gauss_dof.upload(gd.data(), n_gauss, c->stream));
+  HF_TRY(c->gauss_r.upload(gauss_r, n_gauss, c->stream));
+  if (n_bc) {
+    DevBuf<double> v;
+    HF_TRY(v.upload(bc_value, n_bc, c->stream));
+    k_scatter_bc<<<(n_bc + 255) / 256, 256, 0, c->stream>>>(n_bc, c->bc_dofs.p, v.p, c->bcflag.p, c->gfull.p);
+    HF_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  c->op_built = false;
+  return HF_OK;
+}
+
+extern "C" int hf_set_bc_values(hf_ctx* c, const double* bc_value) {
+  if (!c || !bc_value) return hf_fail(HF_ERR_ARG, "hf_set_bc_values: null argument");
+  if (c->n_bc == 0) return HF_OK;
+  cudaSetDevice(c->device);
+  DevBuf<double> v;
+  HF_TRY(v.upload(bc_value, c->n_bc, c->stream));
+  k_scatter_bc<<<(c->n_bc + 255) / 256, 256, 0, c->stream>>>(c->n_bc, c->bc_dofs.p, v.p, nullptr, c->gfull.p);
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return HF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// P1 element matrices, gather assembly (one thread per matrix row, ascending cell order)
+// ---------------------------------------------------------------------------------------
+// Closed forms (exact for affine r; reference forms: run_with_diamond.py:328-335):
+//   axisymmetric  M_ii = |T|(r_i/10 + (r_j+r_k)/30)   M_ij = |T|((r_i+r_j)/30 + r_k/60)
+//                 K_ij = |T| rbar grad phi_i . grad phi_j
+//   planar        M = |T|/12 (1 + delta_ij)           K_ij = |T| grad phi_i . grad phi_j
+//   interval      M = h/6 (1 + delta_ij)              K = +-1/h          (run_no_diamond_1d.py:537-540)
+__global__ void __launch_bounds__(256)
+k_assemble(int N, int nv, int axisym, const double* __restrict__ xy, const int* __restrict__ cells,
+           const double* __restrict__ cm, const double* __restrict__ ck,
+           const int* __restrict__ n2c_ptr, const int* __restrict__ n2c_idx,
+           const int* __restrict__ rowptr, const int* __restrict__ col, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int r0 = rowptr[i], r1 = rowptr[i + 1];
+  for (int k = r0; k < r1; ++k) out[k] = 0.0;
+  for (int a = n2c_ptr[i]; a < n2c_ptr[i + 1]; ++a) {
+    const int e = n2c_idx[a];
+    const double m_e = cm[e], k_e = ck[e];
+    int v[3];
+    double em[3];
+    if (nv == 3) {
+      v[0] = cells[3 * e];
+      v[1] = cells[3 * e + 1];
+      v[2] = cells[3 * e + 2];
+      const int li = (v[0] == i) ? 0 : (v[1] == i) ? 1 : 2;
+      double z[3], r[3];
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        z[t] = xy[2 * v[t]];
+        r[t] = xy[2 * v[t] + 1];
+      }
+      const double bb[3] = {r[1] - r[2], r[2] - r[0], r[0] - r[1]};
+      const double cc[3] = {z[2] - z[1], z[0] - z[2], z[1] - z[0]};
+      const double det = bb[0] * cc[1] - bb[1] * cc[0];
+      const double area = 0.5 * fabs(det);
+      const double rsum = r[0] + r[1] + r[2];
+      const double kw = axisym ? area * rsum / 3.0 : area;
+#pragma unroll
+      for (int lj = 0; lj < 3; ++lj) {
+        double m;
+        if (axisym) {
+          if (lj == li) m = area * (r[li] / 10.0 + (rsum - r[li]) / 30.0);
+          else m = area * ((r[li] + r[lj]) / 30.0 + r[3 - li - lj] / 60.0);
+        } else {
+          m = (lj == li) ? area / 6.0 : area / 12.0;
+        }
+        const double g = (bb[li] / det) * (bb[lj] / det) + (cc[li] / det) * (cc[lj] / det);
+        em[lj] = m_e * m + k_e * (kw * g);
+      }
+    } else {
+      v[0] = cells[2 * e];
+      v[1] = cells[2 * e + 1];
+      v[2] = -1;
+      const int li = (v[0] == i) ? 0 : 1;
+      const double h = fabs(xy[2 * v[1]] - xy[2 * v[0]]);
+#pragma unroll
+      for (int lj = 0; lj < 2; ++lj)
+        em[lj] = m_e * (h / 6.0) * ((lj == li) ? 2.0 : 1.0) + k_e * (1.0 / h) * ((lj == li) ? 1.0 : -1.0);
+      em[2] = 0.0;
+    }
+    for (int lj = 0; lj < nv; ++lj) {
+      const int j = v[lj];
+      int k = r0;
+      while (col[k] != j) ++k;   // j is in the pattern by construction
+      out[k] += em[lj];
+    }
+  }
+}
+
+int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out) {
+  k_assemble<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, c->nv, axisym, c->xy.p, c->cells.p, cm, ck,
+                                                        c->n2c_ptr.p, c->n2c_idx.p, c->rowptr.p, c->col.p, out);
+  HF_CUDA(cudaGetLastError());
+  return HF_OK;
+}
+
+// per-cell coefficients from the tag tables: cm = fm * rho_c(tag), ck = fk * kappa(tag)
+__global__ void k_cell_coef(int E, const int* __restrict__ tag, int nt, const int* __restrict__ tags,
+                            const double* __restrict__ kappa, const double* __restrict__ rhoc,
+                            double fm, double fk, double* __restrict__ cm, double* __restrict__ ck,
+                            int* __restrict__ missing) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int t = tag[e];
+  int f = -1;
+  for (int k = 0; k < nt; ++k)
+    if (tags[k] == t) f = k;
+  if (f < 0) {
+    atomicExch(missing, t + 1);
+    cm[e] = 0.0;
+    ck[e] = 0.0;
+  } else {
+    cm[e] = fm * rhoc[f];
+    ck[e] = fk * kappa[f];
+  }
+}
+
+__global__ void k_fill(int n, double v, double* __restrict__ p) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Dirichlet treatment + Jacobi scaling + sliced-ELL conversion
+// ---------------------------------------------------------------------------------------
+__global__ void k_diag_scale(int N, int Npad, const int* __restrict__ rowptr, const int* __restrict__ col,
+                             const double* __restrict__ val, const unsigned char* __restrict__ bcflag,
+                             int apply_bc, double* __restrict__ scale, int* __restrict__ bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  double s = 1.0;
+  if (i < N && !(apply_bc && bcflag[i])) {
+    double d = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+      if (col[k] == i) d = val[k];
+    if (!(d > 0.0)) {
+      atomicExch(bad, i + 1);
+      d = 1.0;
+    }
+    s = sqrt(d);
+  }
+  scale[i] = s;
+}
+
+__global__ void k_fill_sell(int N, int Npad, const int* __restrict__ rowptr, const int* __restrict__ col,
+                            const double* __restrict__ val, const unsigned char* __restrict__ bcflag,
+                            int apply_bc, const double* __restrict__ scale, const int* __restrict__ slice_ptr,
+                            int* __restrict__ scol, double* __restrict__ sval, double* __restrict__ val_bc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  const int s = i / HF_SLICE, lane = i % HF_SLICE;
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) / HF_SLICE;
+  int len = 0, r0 = 0;
+  if (i < N) {
+    r0 = rowptr[i];
+    len = rowptr[i + 1] - r0;
+  }
+  const bool bci = apply_bc && i < N && bcflag[i];
+  const double si = scale[i];
+  for (int k = 0; k < w; ++k) {
+    int cj = i;
+    double v = 0.0;
+    if (k < len) {
+      cj = col[r0 + k];
+      double a = val[r0 + k];
+      if (apply_bc && (bci || bcflag[cj])) a = (cj == i) ? 1.0 : 0.0;
+      if (val_bc) val_bc[r0 + k] = a;
+      v = a / (si * scale[cj]);
+    }
+    scol[base + k * HF_SLICE + lane] = cj;
+    sval[base + k * HF_SLICE + lane] = v;
+  }
+}
+
+int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out) {
+  const int nsl = c->Npad / HF_SLICE;
+  std::vector<int> sp(nsl + 1, 0);
+  for (int s = 0; s < nsl; ++s) {
+    int w = 0;
+    for (int i = s * HF_SLICE; i < std::min((s + 1) * HF_SLICE, c->N); ++i) w = std::max(w, c->h_rowptr[i + 1] - c->h_rowptr[i]);
+    int64_t next = (int64_t)sp[s] + (int64_t)w * HF_SLICE;
+    if (next > INT32_MAX) return hf_fail(HF_ERR_ARG, "sliced-ELL storage exceeds int32 offsets");
+    sp[s + 1] = (int)next;
+  }
+  op.drop_graphs();
+  op.nslices = nsl;
+  op.padded_nnz = (size_t)sp[nsl];
+  HF_TRY(op.slice_ptr.upload(sp.data(), nsl + 1, c->stream));
+  HF_TRY(op.col.alloc(op.padded_nnz, c->stream));
+  HF_TRY(op.val.alloc(op.padded_nnz, c->stream));
+  HF_TRY(op.scale.alloc(c->Npad, c->stream));
+  if (val_bc_out) HF_TRY(val_bc_out->alloc(c->nnz, c->stream));
+  DevBuf<int> bad;
+  HF_TRY(bad.alloc(1, c->stream));
+  const int g = (c->Npad + 255) / 256;
+  k_diag_scale<<<g, 256, 0, c->stream>>>(c->N, c->Npad, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
+                                         op.scale.p, bad.p);
+  k_fill_sell<<<g, 256, 0, c->stream>>>(c->N, c->Npad, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
+                                        op.scale.p, op.slice_ptr.p, op.col.p, op.val.p, val_bc_out ? val_bc_out->p : nullptr);
+  HF_CUDA(cudaGetLastError());
+  int hbad = 0;
+  HF_TRY(bad.download(&hbad, 1, c->stream));
+  if (hbad) return hf_fail(HF_ERR_STATE, "operator has a non-positive diagonal at row " + std::to_string(hbad - 1) +
+                                             " (unset material or degenerate cell?)");
+  return HF_OK;
+}
+
+static int cell_coefs(hf_ctx* c, double fm, double fk) {
+  const int nt = (int)c->mat_tags.size();
+  if (nt == 0) return hf_fail(HF_ERR_STATE, "call hf_set_materials first");
+  DevBuf<int> tags, miss;
+  DevBuf<double> kap, rc;
+  HF_TRY(tags.upload(c->mat_tags.data(), nt, c->stream));
+  HF_TRY(kap.upload(c->mat_kappa.data(), nt, c->stream));
+  HF_TRY(rc.upload(c->mat_rhoc.data(), nt, c->stream));
+  HF_TRY(miss.alloc(1, c->stream));
+  k_cell_coef<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, c->cell_tag.p, nt, tags.p, kap.p, rc.p, fm, fk, c->cm.p,
+                                                         c->ck.p, miss.p);
+  int hm = 0;
+  HF_TRY(miss.download(&hm, 1, c->stream));
+  if (hm) return hf_fail(HF_ERR_ARG, "cell tag " + std::to_string(hm - 1) + " has no material");
+  return HF_OK;
+}
+
+extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
+  if (!c || c->N == 0) return hf_fail(HF_ERR_STATE, "hf_build_operator: call hf_set_mesh first");
+  if (!(dt > 0.0)) return hf_fail(HF_ERR_ARG, "hf_build_operator: dt must be positive");
+  cudaSetDevice(c->device);
+  c->dt = dt;
+  c->axisym = (c->nv == 3) ? (axisymmetric ? 1 : 0) : 0;
+  HF_TRY(c->valM.alloc(c->nnz, c->stream));
+  HF_TRY(c->valA0.alloc(c->nnz, c->stream));
+  HF_TRY(cell_coefs(c, 1.0, 0.0));
+  HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valM.p));
+  HF_TRY(cell_coefs(c, 1.0, dt));
+  HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valA0.p));
+  HF_TRY(hf_build_sell(c, c->valA0, true, c->opA, &c->valA));
+  c->valM1.release();
+  c->op_built = true;
+  c->proj_built = false;
+  c->last_iters = 0;
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return HF_OK;
+}
+
+extern "C" int hf_get_sizes(hf_ctx* c, int32_t* n_nodes, int64_t* nnz) {
+  if (!c) return hf_fail(HF_ERR_ARG, "null context");
+  if (n_nodes) *n_nodes = c->N;
+  if (nnz) *nnz = c->nnz;
+  return HF_OK;
+}
+
+extern "C" int hf_get_csr(hf_ctx* c, int32_t* rowptr, int32_t* col, double* val_A, double* val_M, double* val_A0) {
+  if (!c || c->N == 0) return hf_fail(HF_ERR_STATE, "hf_get_csr: no mesh");
+  cudaSetDevice(c->device);
+  if (rowptr) HF_TRY(c->rowptr.download(rowptr, c->N + 1, c->stream));
+  if (col) HF_TRY(c->col.download(col, c->nnz, c->stream));
+  if (val_A || val_M || val_A0) {
+    if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_get_csr: operator not built");
+    if (val_A) HF_TRY(c->valA.download(val_A, c->nnz, c->stream));
+    if (val_M) HF_TRY(c->valM.download(val_M, c->nnz, c->stream));
+    if (val_A0) HF_TRY(c->valA0.download(val_A0, c->nnz, c->stream));
+  }
+  return HF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------------------
+extern "C" int hf_set_state(hf_ctx* c, const double* u) {
+  if (!c || !u || c->N == 0) return hf_fail(HF_ERR_ARG, "hf_set_state: bad arguments");
+  cudaSetDevice(c->device);
+  HF_CUDA(cudaMemcpyAsync(c->u.p, u, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_prev = false;
+  return HF_OK;
+}
+
+extern "C" int hf_get_state(hf_ctx* c, double* u) {
+  if (!c || !u || c->N == 0) return hf_fail(HF_ERR_ARG, "hf_get_state: bad arguments");
+  cudaSetDevice(c->device);
+  return c->u.download(u, c->N, c->stream);
+}
+
+extern "C" int hf_get_rhs(hf_ctx* c, double* b) {
+  if (!c || !b || c->N == 0) return hf_fail(HF_ERR_ARG, "hf_get_rhs: bad arguments");
+  cudaSetDevice(c->device);
+  return c->b.download(b, c->N, c->stream);
+}
+
+extern "C" int hf_set_source(hf_ctx* c, const double* s) {
+  if (!c || c->N == 0) return hf_fail(HF_ERR_ARG, "hf_set_source: bad arguments");
+  cudaSetDevice(c->device);
+  if (!s) {
+    c->have_source = false;
+    return HF_OK;
+  }
+  if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_set_source: operator not built");
+  if (c->valM1.n != (size_t)c->nnz) {   // unit-coefficient mass of the linear form dt * s * v
+    HF_TRY(c->valM1.alloc(c->nnz, c->stream));
+    k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 1.0, c->cm.p);
+    k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 0.0, c->ck.p);
+    HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valM1.p));
+  }
+  HF_CUDA(cudaMemcpyAsync(c->source.p, s, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  c->have_source = true;
+  return HF_OK;
+}
+
+extern "C" int hf_set_solver(hf_ctx* c, double rtol, int32_t max_iters, double warm, int32_t mode) {
+  if (!c) return hf_fail(HF_ERR_ARG, "null context");
+  if (!(rtol > 0.0) || max_iters <= 0 || mode < 0 || mode > 2) return hf_fail(HF_ERR_ARG, "hf_set_solver: bad arguments");
+  c->rtol = rtol;
+  c->max_iters = max_iters;
+  c->warm = warm;
+  c->mode = mode;
+  return HF_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// one backward-Euler step
+// ---------------------------------------------------------------------------------------
+// g_j = (amp - t_ic) exp(coeff r_j^2) + t_ic   (reference: run_with_diamond.py:354-359, bc.py:128-137)
+__global__ void k_bc_gauss(int n, const int* __restrict__ dof, const double* __restrict__ r, double amp, double t_ic,
+                           double coeff, double* __restrict__ g) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g[dof[i]] = (amp - t_ic) * exp(coeff * (r[i] * r[i])) + t_ic;
+}
+
+// assemble_vector + apply_lifting + set_bc (reference: run_with_diamond.py:474-479) fused with the
+// start of the solve: b = M u_n [+ dt M1 s] - A0[:,bc] g, b[bc] = g; x0 = warm-started u_n with
+// x0[bc] = g; scaled residual rhat = (b - A x0)/s = ((M u_n)_i - (A0 x0)_i)/s_i on free rows.
+__global__ void __launch_bounds__(HF_BLOCK)
+k_step_init(int N, int Npad, const int* __restrict__ rowptr, const int* __restrict__ col,
+            const double* __restrict__ valM, const double* __restrict__ valA0, const double* __restrict__ valM1,
+            const unsigned char* __restrict__ bcflag, const double* __restrict__ gfull,
+            const double* __restrict__ u, const double* __restrict__ uprev, double warm,
+            const double* __restrict__ src, double dt, const double* __restrict__ scale,
+            double* __restrict__ b, double* __restrict__ xh, double* __restrict__ rh, HfCtrl* __restrict__ c) {
+  __shared__ double sh[HF_BLOCK / 32];
+  double l_rr = 0.0, l_bn = 0.0;
+  for (int i = blockIdx.x * HF_BLOCK + threadIdx.x; i < Npad; i += gridDim.x * HF_BLOCK) {
+    double xv = 0.0, rv = 0.0;
+    if (i < N) {
+      if (bcflag[i]) {
+        const double g = gfull[i];
+        b[i] = g;
+        xv = g;
+      } else {
+        double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+          const int j = col[k];
+          const double m = valM[k], a = valA0[k];
+          const double uj = u[j];
+          double x0j, gj = 0.0;
+          if (bcflag[j]) {
+            gj = gfull[j];
+            x0j = gj;
+          } else {
+            x0j = (warm != 0.0) ? fma(warm, uj - uprev[j], uj) : uj;
+          }
+          t1 = fma(m, uj, t1);
+          if (valM1) t1 = fma(dt * valM1[k], src[j], t1);
+          t2 = fma(a, x0j, t2);
+          t3 = fma(a, gj, t3);
+        }
+        const double s = scale[i];
+        const double bi = t1 - t3;
+        b[i] = bi;
+        const double ui = u[i];
+        xv = s * ((warm != 0.0) ? fma(warm, ui - uprev[i], ui) : ui);
+        rv = (t1 - t2) / s;
+        const double bh = bi / s;
+        l_bn = fma(bh, bh, l_bn);
+        l_rr = fma(rv, rv, l_rr);
+      }
+    }
+    xh[i] = xv;
+    rh[i] = rv;
+  }
+  const double trr = hf_block_sum(l_rr, sh);
+  const double tbn = hf_block_sum(l_bn, sh);
+  if (threadIdx.x == 0) {
+    c->part_rr[0][blockIdx.x] = trr;
+    c->part_bn[blockIdx.x] = tbn;
+  }
+}
+
+__global__ void k_step_finalize(int N, const double* __restrict__ xh, const double* __restrict__ scale,
+                                double* __restrict__ u, double* __restrict__ uprev) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    const double un = xh[i] / scale[i];
+    uprev[i] = u[i];
+    u[i] = un;
+  }
+}
+
+__global__ void k_sample(int n, const int* __restrict__ nodes, const double* __restrict__ u, double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = u[nodes[i]];
+}
+
+static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double coeff, int* iters, double* relres) {
+  if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_step: operator not built");
+  if (use_gauss && c->n_gauss)
+    k_bc_gauss<<<(c->n_gauss + 255) / 256, 256, 0, c->stream>>>(c->n_gauss, c->gauss_dof.p, c->gauss_r.p, amp, t_ic, coeff,
+                                                                c->gfull.p);
+  PcgWork& w = c->ws;
+  const double warm = c->have_prev ? c->warm : 0.0;
+  k_step_init<<<w.grid, HF_BLOCK, 0, c->stream>>>(c->N, c->Npad, c->rowptr.p, c->col.p, c->valM.p, c->valA0.p,
+                                                  c->have_source ? c->valM1.p : nullptr, c->bcflag.p, c->gfull.p, c->u.p,
+                                                  c->uprev.p, warm, c->source.p, c->dt, c->opA.scale.p, c->b.p, w.x.p,
+                                                  w.r.p, w.ctrl.p);
+  HF_CUDA(cudaGetLastError());
+  HF_TRY(hf_pcg_prepare(c));
+  HF_TRY(hf_pcg_solve(c, c->opA, iters, relres));
+  k_step_finalize<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, w.x.p, c->opA.scale.p, c->u.p, c->uprev.p);
+  HF_CUDA(cudaGetLastError());
+  c->have_prev = true;
+  return HF_OK;
+}
+
+extern "C" int hf_step(hf_ctx* c, int32_t use_gauss, double amp, double t_ic, double coeff, int32_t* iters_out,
+                       double* relres_out) {
+  if (!c) return hf_fail(HF_ERR_ARG, "null context");
+  cudaSetDevice(c->device);
+  HF_TRY(step_device(c, use_gauss, amp, t_ic, coeff, iters_out, relres_out));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return HF_OK;
+}
+
+extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic, double coeff, int32_t n_watch,
+                      const int32_t* watch_nodes, double* hist, double* fields, int32_t* iters) {
+  if (!c || n_steps < 0 || (n_steps && !amp) || n_watch < 0 || (n_watch && (!watch_nodes || !hist)))
+    return hf_fail(HF_ERR_ARG, "hf_run: bad arguments");
+  cudaSetDevice(c->device);
+  for (int i = 0; i < n_watch; ++i)
+    if (watch_nodes[i] < 0 || watch_nodes[i] >= c->N) return hf_fail(HF_ERR_ARG, "hf_run: watch node out of range");
+  if (n_watch) {
+    HF_TRY(c->watch.upload(watch_nodes, n_watch, c->stream));
+    if (c->hist.n < (size_t)n_steps * n_watch) HF_TRY(c->hist.alloc((size_t)n_steps * n_watch, c->stream));
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    int it = 0;
+    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr));
+    if (iters) iters[s] = it;
+    if (n_watch)
+      k_sample<<<(n_watch + 255) / 256, 256, 0, c->stream>>>(n_watch, c->watch.p, c->u.p, c->hist.p + (size_t)s * n_watch);
+    if (fields)
+      HF_CUDA(cudaMemcpyAsync(fields + (size_t)s * c->N, c->u.p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (n_watch && n_steps)
+    HF_CUDA(cudaMemcpyAsync(hist, c->hist.p, sizeof(double) * (size_t)n_steps * n_watch, cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return HF_OK;
+}
+
+extern "C" int hf_sample(hf_ctx* c, int32_t n, const int32_t* nodes, double* out) {
+  if (!c || n < 0 || (n && (!nodes || !out))) return hf_fail(HF_ERR_ARG, "hf_sample: bad arguments");
+  if (n == 0) return HF_OK;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < n; ++i)
+    if (nodes[i] < 0 || nodes[i] >= c->N) return hf_fail(HF_ERR_ARG, "hf_sample: node out of range");
+  DevBuf<int> d;
+  DevBuf<double> o;
+  HF_TRY(d.upload(nodes, n, c->stream));
+  HF_TRY(o.alloc(n, c->stream));
+  k_sample<<<(n + 255) / 256, 256, 0, c->stream>>>(n, d.p, c->u.p, o.p);
+  return o.download(out, n, c->stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// SpMV through the production kernel (parity + roofline tests)
+// ---------------------------------------------------------------------------------------
+__global__ void k_scale_in(int N, int Npad, const double* __restrict__ x, const double* __restrict__ s, double* __restrict__ o) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Npad) o[i] = (i < N) ? x[i] * s[i] : 0.0;
+}
+__global__ void k_scale_out(int N, const double* __restrict__ q, const double* __restrict__ s, double* __restrict__ y) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) y[i] = q[i] * s[i];
+}
+__global__ void k_ctrl_force(HfCtrl* c, int nparts) {
+  for (int i = threadIdx.x; i < HF_MAX_PART; i += blockDim.x) c->part_rr[0][i] = 1.0;
+  if (threadIdx.x == 0) {
+    c->thr = -1.0;
+    c->done = 0;
+    c->itA = 0;
+    c->itB = 0;
+    c->nparts = nparts;
+  }
+}
+int hf_spmv_device(hf_ctx* c, const SellOp& op);   // hf_pcg.cu
+
+extern "C" int hf_spmv(hf_ctx* c, const double* x, double* y) {
+  if (!c || !x || !y) return hf_fail(HF_ERR_ARG, "hf_spmv: null argument");
+  if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_spmv: operator not built");
+  cudaSetDevice(c->device);
+  PcgWork& w = c->ws;
+  DevBuf<double> dx;
+  HF_TRY(dx.upload(x, c->N, c->stream));
+  const int g = (c->Npad + 255) / 256;
+  k_scale_in<<<g, 256, 0, c->stream>>>(c->N, c->Npad, dx.p, c->opA.scale.p, w.r.p);
+  k_ctrl_force<<<1, 256, 0, c->stream>>>(w.ctrl.p, w.grid);
+  HF_TRY(hf_spmv_device(c, c->opA));
+  k_scale_out<<<g, 256, 0, c->stream>>>(c->N, w.q.p, c->opA.scale.p, dx.p);
+  HF_CUDA(cudaGetLastError());
+  return dx.download(y, c->N, c->stream);
+}
+
+// ---------------------------------------------------------------------------------------
+// r-weighted L2 projection of grad(u) onto vector P1 (reference: run_no_diamond.py:471-491, :544-550)
+// ---------------------------------------------------------------------------------------
+// load b_c[i] = sum_T (d_c u)_T |T| (2 r_i + r_j + r_k)/12, written Jacobi-scaled into rz / rr.
+__global__ void __launch_bounds__(256)
+k_grad_load(int N, int Npad, const double* __restrict__ xy, const int* __restrict__ cells,
+            const int* __restrict__ n2c_ptr, const int* __restrict__ n2c_idx, const double* __restrict__ u,
+            const double* __restrict__ scale, double* __restrict__ bz, double* __restrict__ br) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  double az = 0.0, ar = 0.0;
+  if (i < N) {
+    for (int a = n2c_ptr[i]; a < n2c_ptr[i + 1]; ++a) {
+      const int e = n2c_idx[a];
+      const int v0 = cells[3 * e], v1 = cells[3 * e + 1], v2 = cells[3 * e + 2];
+      const double z0 = xy[2 * v0], r0 = xy[2 * v0 + 1], z1 = xy[2 * v1], r1 = xy[2 * v1 + 1], z2 = xy[2 * v2],
+                   r2 = xy[2 * v2 + 1];
+      const double b0 = r1 - r2, b1 = r2 - r0, b2 = r0 - r1;
+      const double c0 = z2 - z1, c1 = z0 - z2, c2 = z1 - z0;
+      const double det = b0 * c1 - b1 * c0;
+      const double area = 0.5 * fabs(det);
+      const double u0 = u[v0], u1 = u[v1], u2 = u[v2];
+      const double dz = (b0 / det) * u0 + (b1 / det) * u1 + (b2 / det) * u2;
+      const double dr = (c0 / det) * u0 + (c1 / det) * u1 + (c2 / det) * u2;
+      const double ri = (v0 == i) ? r0 : (v1 == i) ? r1 : r2;
+      const double wgt = area * (ri + (r0 + r1 + r2)) / 12.0;
+      az = fma(wgt, dz, az);
+      ar = fma(wgt, dr, ar);
+    }
+    const double s = scale[i];
+    az /= s;
+    ar /= s;
+  }
+  bz[i] = az;
+  br[i] = ar;
+}
+
+__global__ void k_store_comp(int N, const double* __restrict__ xh, const double* __restrict__ scale, int comp,
+                             double* __restrict__ g2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) g2[2 * i + comp] = xh[i] / scale[i];
+}
+
+extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) {
+  if (!c || !grad) return hf_fail(HF_ERR_ARG, "hf_project_gradient: null argument");
+  if (c->N == 0 || c->nv != 3) return hf_fail(HF_ERR_STATE, "hf_project_gradient: needs a triangle mesh");
+  cudaSetDevice(c->device);
+  if (!c->proj_built) {
+    DevBuf<double> vals;
+    HF_TRY(vals.alloc(c->nnz, c->stream));
+    k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 1.0, c->cm.p);
+    k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 0.0, c->ck.p);
+    HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, 1, vals.p));
+    HF_TRY(hf_build_sell(c, vals, false, c->opMr, nullptr));
+    HF_TRY(c->proj_b.alloc((size_t)2 * c->Npad, c->stream));
+    HF_TRY(c->proj_g.alloc((size_t)2 * c->N, c->stream));
+    c->proj_built = true;
+  }
+  PcgWork& w = c->ws;
+  const int g = (c->Npad + 255) / 256;
+  k_grad_load<<<g, 256, 0, c->stream>>>(c->N, c->Npad, c->xy.p, c->cells.p, c->n2c_ptr.p, c->n2c_idx.p, c->u.p,
+                                        c->opMr.scale.p, c->proj_b.p, c->proj_b.p + c->Npad);
+  HF_CUDA(cudaGetLastError());
+  const int keep = c->last_iters;
+  int total = 0;
+  for (int comp = 0; comp < 2; ++comp) {
+    HF_CUDA(cudaMemcpyAsync(w.r.p, c->proj_b.p + (size_t)comp * c->Npad, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice,
+                            c->stream));
+    HF_CUDA(cudaMemsetAsync(w.x.p, 0, sizeof(double) * c->Npad, c->stream));
+    HF_TRY(hf_pcg_prepare_from_r(c));
+    int it = 0;
+    c->last_iters = 40;
+    HF_TRY(hf_pcg_solve(c, c->opMr, &it, nullptr));
+    total += it;
+    k_store_comp<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, w.x.p, c->opMr.scale.p, comp, c->proj_g.p);
+  }
+  c->last_iters = keep;
+  if (iters_out) *iters_out = total;
+  return c->proj_g.download(grad, (size_t)2 * c->N, c->stream);
+}

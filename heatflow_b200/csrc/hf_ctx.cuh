@@ -1,0 +1,208 @@
+// heatflow_b200 - shared context, device buffers and reduction helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/heatflow_b200.h"
+
+#define HF_BLOCK 256          // threads per CTA of the streaming kernels (8 warps)
+#define HF_SLICE 32           // rows per sliced-ELL slice = one warp, one row per lane
+#define HF_MAX_PART 2368      // max CTAs of a reduction-producing kernel (148 SMs x 16)
+
+extern thread_local std::string hf_err_msg;
+int hf_fail(int code, const std::string& msg);
+
+#define HF_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return hf_fail(HF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));    \
+  } while (0)
+
+#define HF_TRY(call)                 \
+  do {                               \
+    int rc__ = (call);               \
+    if (rc__ != HF_OK) return rc__;  \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  // zero-filled allocation; the fill is ordered on stream `s` (the context stream is
+  // non-blocking, so a legacy-stream cudaMemset could land after later kernels on `s`)
+  int alloc(size_t count, cudaStream_t s) {
+    release();
+    n = count;
+    if (count == 0) return HF_OK;
+    HF_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    HF_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), s));
+    return HF_OK;
+  }
+  int upload(const T* h, size_t count, cudaStream_t s) {
+    if (count != n || !p) HF_TRY(alloc(count, s));
+    if (count) HF_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    return HF_OK;
+  }
+  int download(T* h, size_t count, cudaStream_t s) const {
+    if (count > n) return hf_fail(HF_ERR_ARG, "download larger than buffer");
+    if (count) HF_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    HF_CUDA(cudaStreamSynchronize(s));
+    return HF_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// Device-side control block of one PCG solve.  Every CTA reduces the partial sums itself (fixed
+// order => bit-reproducible), so alpha/beta/convergence never touch the host.
+struct HfCtrl {
+  double thr;        // rtol^2 * ||b_free||^2 in the Jacobi-scaled norm
+  double bn2;        // ||b_free||^2
+  double rr;         // ||r||^2 when the solve stopped
+  int done;          // set by the SpMV kernel once rr <= thr
+  int itA;           // iteration counter read by the SpMV kernel (written by the update kernel)
+  int itB;           // copy read by the update kernel (written by the SpMV kernel)
+  int nparts;        // number of valid partial sums (= grid of the producing kernels)
+  double part_rr[2][HF_MAX_PART];
+  double part_pq[HF_MAX_PART];
+  double part_bn[HF_MAX_PART];
+};
+
+// Sliced-ELL view of a Jacobi-scaled symmetric operator  D^-1/2 A D^-1/2.
+struct SellView {
+  int nslices;
+  const int* __restrict__ slice_ptr;   // [nslices+1] element offsets
+  const int* __restrict__ col;         // [slice_ptr[nslices]]
+  const double* __restrict__ val;
+};
+
+struct SellOp {
+  int nslices = 0;
+  size_t padded_nnz = 0;
+  DevBuf<int> slice_ptr, col;
+  DevBuf<double> val;
+  DevBuf<double> scale;                // s_i = sqrt(diag) (1 on Dirichlet rows)
+  mutable cudaGraphExec_t chunk_exec[3] = {nullptr, nullptr, nullptr};   // captured PCG iteration chunks
+  SellView view() const { return SellView{nslices, slice_ptr.p, col.p, val.p}; }
+  void drop_graphs() const {
+    for (auto& g : chunk_exec) {
+      if (g) cudaGraphExecDestroy(g);
+      g = nullptr;
+    }
+  }
+  ~SellOp() { drop_graphs(); }
+};
+
+struct PcgWork {
+  DevBuf<double> x, r, p0, p1, q;
+  DevBuf<HfCtrl> ctrl;
+  HfCtrl* h_ctrl = nullptr;            // pinned mirror of the control-block header
+  int grid = 0;
+};
+
+struct EnsState;
+
+struct hf_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  // mesh
+  int N = 0, E = 0, nv = 3, Npad = 0;
+  DevBuf<double> xy;
+  DevBuf<int> cells, cell_tag;
+  DevBuf<int> n2c_ptr, n2c_idx;
+  std::vector<int> h_rowptr, h_col;
+  DevBuf<int> rowptr, col;
+  int64_t nnz = 0;
+  // materials
+  std::vector<int> mat_tags;
+  std::vector<double> mat_kappa, mat_rhoc;
+  DevBuf<double> cm, ck;               // per-cell coefficients fed to the assembly kernel
+  // boundary conditions
+  int n_bc = 0, n_gauss = 0;
+  DevBuf<int> bc_dofs, gauss_dof;
+  DevBuf<double> gauss_r;
+  DevBuf<unsigned char> bcflag;
+  DevBuf<double> gfull;                // g on Dirichlet dofs, 0 elsewhere
+  // operator
+  bool op_built = false;
+  double dt = 0.0;
+  int axisym = 1;
+  DevBuf<double> valM, valA0, valA, valM1;
+  SellOp opA;
+  // projection operator (built lazily)
+  bool proj_built = false;
+  SellOp opMr;
+  DevBuf<double> proj_b, proj_g;
+  // state
+  DevBuf<double> u, uprev, b, source;
+  bool have_prev = false, have_source = false;
+  // solver
+  double rtol = 1e-14, warm = 0.0;
+  int max_iters = 20000, mode = 0, last_iters = 0;
+  PcgWork ws;
+  DevBuf<double> hist;
+  DevBuf<int> watch;
+  DevBuf<unsigned char> flush;         // L2 flush buffer for hf_bench_kernels
+  EnsState* ens = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double hf_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA, result returned to every thread; fixed order => deterministic.
+// `sh` must hold HF_BLOCK/32 doubles; may be reused after the call returns.
+__device__ __forceinline__ double hf_block_sum(double v, double* sh) {
+  v = hf_warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < HF_BLOCK / 32; ++i) t += sh[i];
+  return t;
+}
+
+// Sum of n partial sums stored in global memory, same value in every thread of every CTA.
+__device__ __forceinline__ double hf_sum_parts(const double* part, int n, double* sh) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += HF_BLOCK) v += __ldcg(part + i);
+  return hf_block_sum(v, sh);
+}
+
+__device__ __forceinline__ double hf_ld_stream(const double* p) {
+  double v;
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int hf_ld_stream(const int* p) {
+  int v;
+  asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// shared between translation units
+int hf_pcg_alloc(hf_ctx* c);
+int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out);
+int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out);
+int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out);
+void hf_ens_free(hf_ctx* c);

@@ -1,0 +1,186 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the scipy oracle on the same inputs.
+
+Bars (BASELINE.json north_star): dof map and sparsity pattern bit-exact; fp64 temperatures
+within 1e-10 relative at every output step.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import build_case, make_oracle, make_solver
+from oracle import heat_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+RTOL_FIELD = 1e-10   # the tolerance north_star states for temperature histories
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.fixture(scope="module")
+def small_nd():
+    return build_case("geballe_no_diamond", 8.0)
+
+
+@pytest.fixture(scope="module")
+def small_wd():
+    return build_case("geballe_with_diamond", 8.0)
+
+
+@pytest.mark.parametrize("name", ["geballe_no_diamond", "geballe_with_diamond"])
+def test_pattern_bit_exact_and_values(name):
+    c = build_case(name, 8.0)
+    s = make_solver(c)
+    O = make_oracle(c)
+    rowptr, col, A, M, A0 = s.csr()
+    assert rowptr.dtype == np.int32 and col.dtype == np.int32
+    assert np.array_equal(rowptr, O.rowptr)
+    assert np.array_equal(col, O.col)
+    for got, want in ((M, O.M.data), (A0, O.A0.data), (A, O.A.data)):
+        row_of = np.repeat(np.arange(len(c.nodes)), np.diff(rowptr))
+        rowmax = np.maximum.reduceat(np.abs(want), rowptr[:-1])[row_of]
+        assert np.all(np.abs(got - want) <= 1e-13 * rowmax)
+    # Dirichlet rows: exactly identity (dolfinx convention, clean_with_ir.ipynb:724)
+    Acsr = sp.csr_matrix((A, col, rowptr), shape=(len(c.nodes),) * 2)
+    d = Acsr.diagonal()
+    assert np.all(d[c.bc_dofs] == 1.0)
+    assert np.all(np.abs(Acsr[c.bc_dofs]).sum(axis=1) == 1.0)
+    assert abs(Acsr - Acsr.T).max() == 0.0
+    s.close()
+
+
+def test_spmv_matches_scipy(small_wd):
+    c = small_wd
+    s = make_solver(c)
+    O = make_oracle(c)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(len(c.nodes))
+    y = s.spmv(x)
+    want = O.A @ x
+    scale = np.abs(O.A) @ np.abs(x)
+    assert np.all(np.abs(y - want) <= 1e-14 * scale)
+    s.close()
+
+
+def test_rhs_and_single_step(small_nd):
+    c = small_nd
+    s = make_solver(c)
+    O = make_oracle(c)
+    # a heated step (amplitude well above ic) from a non-trivial state
+    rng = np.random.default_rng(1)
+    u0 = c.ic + 50.0 * rng.random(len(c.nodes))
+    s.set_state(u0)
+    O.u = u0.copy()
+    k = 20
+    t = (k + 1) * c.dt
+    its, rel = s.step(amp=c.amps[k], t_ic=c.ic, coeff=c.coeff)
+    uo = O.step(t)
+    assert its > 0 and rel <= 1e-14
+    b = s.get_rhs()
+    scale = abs(O.M) @ np.abs(u0) + abs(O.A0) @ np.abs(O.g)      # row-wise magnitude of the terms summed
+    free = np.setdiff1d(np.arange(len(c.nodes)), c.bc_dofs)
+    assert np.all(np.abs(b - O.b)[free] <= 1e-14 * scale[free])
+    assert np.array_equal(b[c.bc_dofs], O.b[c.bc_dofs]) or rel_err(b[c.bc_dofs], O.b[c.bc_dofs]) < 1e-15
+    assert rel_err(s.get_state(), uo) <= RTOL_FIELD
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["geballe_no_diamond", "geballe_with_diamond"])
+def test_history_every_step(name):
+    c = build_case(name, 8.0)
+    s = make_solver(c)
+    O = make_oracle(c)
+    watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.9e-6, 0.0)])
+    hist, iters, fields = s.run(c.amps, c.ic, c.coeff, watch, keep_fields=True)
+    ohist, ofields = O.run(c.num_steps, watch, keep_fields=True)
+    worst = max(rel_err(f, of) for f, of in zip(fields, ofields))
+    assert worst <= RTOL_FIELD, worst
+    # pointwise relative error too (temperatures are >= 300 K everywhere)
+    assert max(np.abs(f / of - 1).max() for f, of in zip(fields, ofields)) <= RTOL_FIELD
+    assert np.abs(hist / ohist - 1).max() <= RTOL_FIELD
+    assert np.array_equal(hist, np.array([f[watch] for f in fields]))
+    assert iters.max() > 0
+    s.close()
+
+
+def test_constant_state_invariance(small_wd):
+    # all BCs = ic and u0 = ic: the state must stay ic to rounding
+    c = small_wd
+    s = make_solver(c)
+    hist, iters, fields = s.run(np.full(5, c.ic), c.ic, c.coeff, [0], keep_fields=True)
+    assert np.abs(fields[-1] / c.ic - 1).max() < 1e-12
+    s.close()
+
+
+def test_full_size_no_diamond_vs_oracle():
+    # configs[1] at the cfg's own mesh sizes (~1.1e5 dofs, 40 steps)
+    c = build_case("geballe_no_diamond", 1.0)
+    s = make_solver(c)
+    O = make_oracle(c)
+    watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
+    hist, iters, _ = s.run(c.amps, c.ic, c.coeff, watch)
+    ohist, _ = O.run(c.num_steps, watch)
+    assert np.abs(hist / ohist - 1).max() <= RTOL_FIELD
+    assert rel_err(s.get_state(), O.u) <= RTOL_FIELD
+    s.close()
+
+
+def test_run_is_bit_reproducible(small_nd):
+    c = small_nd
+    out = []
+    for _ in range(2):
+        s = make_solver(c)
+        hist, iters, _ = s.run(c.amps[:25], c.ic, c.coeff, [5, 50])
+        out.append((hist, iters, s.get_state()))
+        s.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][2], out[1][2])
+
+
+def test_warm_start_same_answer(small_wd):
+    c = small_wd
+    a = make_solver(c, warm=0.0)
+    b = make_solver(c, warm=1.0)
+    ha, ia, _ = a.run(c.amps[:40], c.ic, c.coeff, [3])
+    hb, ib, _ = b.run(c.amps[:40], c.ic, c.coeff, [3])
+    assert rel_err(a.get_state(), b.get_state()) <= 1e-11
+    a.close()
+    b.close()
+
+
+def test_gradient_projection(small_nd):
+    c = small_nd
+    s = make_solver(c)
+    O = make_oracle(c)
+    s.run(c.amps[:25], c.ic, c.coeff, [])
+    O.run(25)
+    P = ho.GradientProjector(c.nodes, c.tris)
+    want = P.project(s.get_state())
+    got = s.project_gradient()
+    scale = np.abs(want).max(axis=0)
+    assert np.all(np.abs(got - want).max(axis=0) <= 1e-9 * scale)
+    s.close()
+
+
+def test_error_paths(small_nd):
+    from heatflow_b200._lib import HeatflowError
+    from heatflow_b200.solver import HeatSolver
+    c = small_nd
+    s = HeatSolver(0)
+    with pytest.raises(HeatflowError):
+        s.step(amp=300.0, t_ic=300.0, coeff=-1.0)          # no mesh / operator yet
+    bad = c.tris.copy()
+    bad[0, 0] = len(c.nodes) + 5
+    with pytest.raises(HeatflowError):
+        s.set_mesh(c.nodes, bad, c.cell_tag)
+    s.set_mesh(c.nodes, c.tris, c.cell_tag)
+    s.set_materials(c.tags[:-1], c.kappa_t[:-1], c.rhoc_t[:-1])  # one tag without material
+    s.set_bcs(c.bc_dofs, c.bc_value, c.gauss_slot, c.gauss_r)
+    with pytest.raises(HeatflowError):
+        s.build_operator(c.dt, True)
+    with pytest.raises(HeatflowError):
+        s.set_bcs(c.bc_dofs[::-1].copy(), c.bc_value, c.gauss_slot, c.gauss_r)  # unsorted
+    s.close()
