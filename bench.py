@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Benchmark of the heat-conduction hot path (contract: see the round prompt / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one backward-Euler time step (Gaussian BC update, RHS, Jacobi-PCG solve) of
+``cfgs/geballe_with_diamond.yaml`` on the mesh at the cfg's own sizes (N ~ 1.4e5 dofs).
+At N GPUs every rank runs one independent simulation of the sweep (its own k_sample / fwhm
+variant) - no data-path collective, one final gather of the watcher histories ("weak").
+``value`` = DOF-timesteps/s of the whole job with the state resident in HBM, device-timed;
+``e2e`` = the same through the C-ABI with host buffers (state upload, amplitudes in, watcher
+histories and final field out) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "geballe_with_diamond"
+METRIC = "DOF-timesteps/sec, geballe_with_diamond"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def variant_params(case, index):
+    """Sweep variant `index` of the 64 x 64 (k, fwhm) grid of config #5 (parameter_sweep.py:221-222)."""
+    if index == 0:
+        return None                                    # the cfg's own k_sample / fwhm
+    ks = np.logspace(0.0, 2.0, 64)
+    fw = np.logspace(-6.0, -4.0, 64)
+    return float(ks[(index * 7) % 64]), float(fw[(index * 11) % 64])
+
+
+def build(index, size_scale=1.0):
+    from helpers import build_case
+    from heatflow_b200 import problem
+    c = build_case(WORKLOAD, size_scale)
+    v = variant_params(c, index)
+    if v is not None:
+        k, fwhm = v
+        c.kappa_t = c.kappa_t.copy()
+        c.kappa_t[[m.name for m in c.mats].index("p_sample")] = k
+        c.kappa_c = c.kappa_t[c.cell_tag - 1]
+        c.fwhm, c.coeff = fwhm, problem.gaussian_coeff(fwhm)
+    return c
+
+
+def oracle_loop(c, steps, warmup):
+    """CPU arm: the scipy sparse-LU oracle on this host, 1 thread (SuperLU is sequential)."""
+    from helpers import make_oracle
+    t0 = time.perf_counter()
+    O = make_oracle(c)
+    t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    O.factorize()
+    t_fac = time.perf_counter() - t0
+    for s in range(warmup):
+        O.step((s + 1) * c.dt)
+    t0 = time.perf_counter()
+    for s in range(warmup, warmup + steps):
+        O.step((s + 1) * c.dt)
+    t_loop = time.perf_counter() - t0
+    return t_loop, t_asm, t_fac, O
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    c = build(0)
+    n = len(c.nodes)
+    steps = min(args.steps, c.num_steps - args.warmup)
+    t_loop, t_asm, t_fac, _ = oracle_loop(c, steps, args.warmup)
+    value = n * steps / t_loop
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "DOF-timesteps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_loop / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: 1 simulation, N={n} dofs, cfg mesh sizes, in-repo mesher"},
+        "cpu_baseline": {"value": value, "unit": "DOF-timesteps/s", "cores": 1, "kind": "port",
+                         "sample": f"{steps} time steps after {args.warmup} warm-up steps; scipy splu factorised once "
+                                   f"outside the timed loop (assembly {t_asm:.2f} s, factorisation {t_fac:.2f} s)"},
+        "e2e": {"value": value, "unit": "DOF-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def kernel_roofline(solver, n, nnz, peak, peak_src, traffic=None):
+    ms_spmv, ms_upd = solver.bench_kernels(reps=30, flush_l2=True)
+    alg = 12.0 * nnz + 4.0 * n / 32 + 32.0 * n        # SpMV kernel: matrix + slice ptr + r, p_old, p_new, q
+    ach = alg / (ms_spmv * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_pcg_spmv", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_us": ms_spmv * 1e3,
+            "update_kernel_us": ms_upd * 1e3, "update_kernel_GBs": 48.0 * n / (ms_upd * 1e-3) / 1e9,
+            "peak_source": peak_src, "how": "CUDA events on the launching stream, 30 launches, L2 flushed between launches"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from scipy.spatial import cKDTree
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    c = build(rank)
+    n = len(c.nodes)
+    steps = min(args.steps, c.num_steps)
+    from heatflow_b200.solver import HeatSolver
+    s = HeatSolver(local_rank)
+    s.set_mesh(c.nodes, c.tris, c.cell_tag)
+    s.set_materials(c.tags, c.kappa_t, c.rhoc_t)
+    s.set_bcs(c.bc_dofs, c.bc_value, c.gauss_slot, c.gauss_r)
+    s.build_operator(c.dt, True)
+    s.set_solver(rtol=args.rtol, warm=args.warm_start)
+    _, nnz = s.sizes()
+    tree = cKDTree(c.nodes)
+    watch = np.array([tree.query(p)[1] for p in [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0)]], dtype=np.int32)
+    u0 = np.full(n, c.ic)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: W steps from the heated part of the curve (graphs captured, clocks up)
+    s.set_state(u0)
+    s.run(c.amps[20:20 + max(args.warmup, 3)], c.ic, c.coeff, watch)
+
+    # ---- timed region 1: state resident in HBM, device-timed (CUDA events on the solver stream)
+    s.set_state(u0)
+    launches0 = s.stats()["launches"]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        hist, iters, _ = s.run(c.amps[:steps], c.ic, c.coeff, watch)
+        barrier()
+    st = s.stats()
+    dev_ms = st["run_ms"]
+    launches = st["launches"] - launches0
+
+    # ---- timed region 2: end to end through the C-ABI with host buffers
+    barrier()
+    t0 = time.perf_counter()
+    s.set_state(u0)                                        # H2D: N*8 bytes
+    hist2, iters2, _ = s.run(c.amps[:steps], c.ic, c.coeff, watch)   # H2D amps, D2H watcher history
+    final = s.get_state()                                  # D2H: N*8 bytes
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(torch.from_numpy(hist).cuda()) for _ in range(world)] if rank == 0 else None
+        dist.gather(torch.from_numpy(hist).cuda(), gathered, dst=0)     # the single final gather
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        s.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    roof = kernel_roofline(s, n, nnz, peak, peak_src)
+    line = {
+        "metric": METRIC, "value": world * n * steps / (dev_ms * 1e-3), "unit": "DOF-timesteps/s", "n_gpus": world,
+        "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: 1 simulation per GPU (sweep variant = rank), N={n} dofs, nnz={nnz}, "
+                               f"cfg mesh sizes, in-repo mesher; rtol={args.rtol:g}",
+                   "l2": "working set (~20 MB) is smaller than L2; kernel roofline timed with an L2 flush between launches",
+                   "pcg_iterations_total": int(iters.sum()), "pcg_iterations_max": int(iters.max())},
+        "e2e": {"value": world * n * steps / (e2e_ms * 1e-3), "unit": "DOF-timesteps/s",
+                "h2d_bytes_per_step": (n * 8 + steps * 8 + len(watch) * 4) / steps,
+                "d2h_bytes_per_step": (n * 8 + steps * len(watch) * 8 + steps * 4) / steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roof,
+    }
+    # >= 1 M-dof mesh (north_star target for the SpMV roofline): same cfg, size_scale 0.35
+    if not args.skip_large:
+        cl = build(0, size_scale=0.35)
+        sl = HeatSolver(local_rank)
+        sl.set_mesh(cl.nodes, cl.tris, cl.cell_tag)
+        sl.set_materials(cl.tags, cl.kappa_t, cl.rhoc_t)
+        sl.set_bcs(cl.bc_dofs, cl.bc_value, cl.gauss_slot, cl.gauss_r)
+        sl.build_operator(cl.dt, True)
+        sl.set_solver(rtol=args.rtol)
+        sl.set_state(np.full(len(cl.nodes), cl.ic))
+        sl.run(cl.amps[20:22], cl.ic, cl.coeff, [0])
+        nl, nnzl = sl.sizes()
+        traffic_1m = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic_1m = json.load(f).get("k_pcg_spmv_1m")
+        except Exception:
+            pass
+        line["roofline_1m"] = dict(kernel_roofline(sl, nl, nnzl, peak, peak_src, traffic_1m), n_dofs=nl, nnz=nnzl)
+        sl.close()
+    # CPU baseline on this host (bounded sample)
+    if not args.skip_cpu:
+        cb_steps = min(20, steps)
+        t_loop, t_asm, t_fac, O = oracle_loop(c, cb_steps, 1)
+        line["cpu_baseline"] = {"value": n * cb_steps / t_loop, "unit": "DOF-timesteps/s", "cores": 1, "kind": "port",
+                                "sample": f"{cb_steps} time steps of the same simulation after 1 warm-up step, scipy splu "
+                                          f"(SuperLU, sequential) factorised once outside the loop "
+                                          f"(assembly {t_asm:.2f} s, factorisation {t_fac:.2f} s); host has {os.cpu_count()} cores"}
+    line["parity_check"] = {"e2e_equals_device_run": bool(np.array_equal(hist, hist2))}
+    print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rtol", type=float, default=1e-14)
+    ap.add_argument("--warm-start", type=float, default=0.0)
+    ap.add_argument("--skip-large", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,7 @@ SIGNATURES = {
     "hf_get_rhs": (C.c_int, [_vp, _vp]),
     "hf_run": (C.c_int, [_vp, _i32, _vp, _f64, _f64, _i32, _vp, _vp, _vp, _vp]),
     "hf_sample": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "hf_get_stats": (C.c_int, [_vp, _vp]),
     "hf_project_gradient": (C.c_int, [_vp, _vp, C.POINTER(_i32)]),
     "hf_spmv": (C.c_int, [_vp, _vp, _vp]),
     "hf_bench_kernels": (C.c_int, [_vp, _i32, _i32, _vp]),

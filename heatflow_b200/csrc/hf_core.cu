@@ -44,8 +44,9 @@ extern "C" hf_ctx* hf_create(int device) {
   c->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    hf_fail(HF_ERR_CUDA, "hf_create: cudaStreamCreate failed");
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    hf_fail(HF_ERR_CUDA, "hf_create: cudaStreamCreate/cudaEventCreate failed");
     delete c;
     return nullptr;
   }
@@ -60,6 +61,8 @@ extern "C" void hf_destroy(hf_ctx* c) {
   if (c->ws.h_ctrl) cudaFreeHost(c->ws.h_ctrl);
   c->opA.drop_graphs();
   c->opMr.drop_graphs();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
   cudaStream_t s = c->stream;
   delete c;
   cudaStreamDestroy(s);
@@ -575,6 +578,7 @@ __global__ void k_sample(int n, const int* __restrict__ nodes, const double* __r
 
 static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double coeff, int* iters, double* relres) {
   if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_step: operator not built");
+  c->stat_launches += 2 + ((use_gauss && c->n_gauss) ? 1 : 0);
   if (use_gauss && c->n_gauss)
     k_bc_gauss<<<(c->n_gauss + 255) / 256, 256, 0, c->stream>>>(c->n_gauss, c->gauss_dof.p, c->gauss_r.p, amp, t_ic, coeff,
                                                                 c->gfull.p);
@@ -613,18 +617,33 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
     HF_TRY(c->watch.upload(watch_nodes, n_watch, c->stream));
     if (c->hist.n < (size_t)n_steps * n_watch) HF_TRY(c->hist.alloc((size_t)n_steps * n_watch, c->stream));
   }
+  HF_CUDA(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < n_steps; ++s) {
     int it = 0;
     HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr));
     if (iters) iters[s] = it;
+    if (n_watch) c->stat_launches += 1;
     if (n_watch)
       k_sample<<<(n_watch + 255) / 256, 256, 0, c->stream>>>(n_watch, c->watch.p, c->u.p, c->hist.p + (size_t)s * n_watch);
     if (fields)
       HF_CUDA(cudaMemcpyAsync(fields + (size_t)s * c->N, c->u.p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
   }
+  HF_CUDA(cudaEventRecord(c->ev1, c->stream));
   if (n_watch && n_steps)
     HF_CUDA(cudaMemcpyAsync(hist, c->hist.p, sizeof(double) * (size_t)n_steps * n_watch, cudaMemcpyDeviceToHost, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  HF_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->stat_run_ms = ms;
+  return HF_OK;
+}
+
+extern "C" int hf_get_stats(hf_ctx* c, double* st) {
+  if (!c || !st) return hf_fail(HF_ERR_ARG, "hf_get_stats: null argument");
+  st[0] = c->stat_run_ms;
+  st[1] = (double)c->stat_launches;
+  st[2] = (double)c->stat_iters;
+  st[3] = c->stat_relres;
   return HF_OK;
 }
 

@@ -152,6 +152,10 @@ struct hf_ctx {
   // solver
   double rtol = 1e-14, warm = 0.0;
   int max_iters = 20000, mode = 0, last_iters = 0;
+  // counters (hf_get_stats)
+  double stat_run_ms = 0.0, stat_relres = 0.0;
+  unsigned long long stat_launches = 0, stat_iters = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   PcgWork ws;
   DevBuf<double> hist;
   DevBuf<int> watch;

@@ -203,6 +203,7 @@ int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out
       HF_CUDA(cudaGraphLaunch(op.chunk_exec[k], c->stream));
       want -= kChunk[k];
       launched += kChunk[k];
+      c->stat_launches += 2ull * kChunk[k];
     }
     HF_CUDA(cudaMemcpyAsync(w.h_ctrl, w.ctrl.p, hdr, cudaMemcpyDeviceToHost, c->stream));
     HF_CUDA(cudaStreamSynchronize(c->stream));
@@ -219,6 +220,8 @@ int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out
   }
   const int its = w.h_ctrl->itA;
   c->last_iters = its;
+  c->stat_iters += its;
+  c->stat_relres = (w.h_ctrl->bn2 > 0.0) ? std::sqrt(w.h_ctrl->rr / w.h_ctrl->bn2) : 0.0;
   if (iters_out) *iters_out = its;
   if (relres_out) *relres_out = (w.h_ctrl->bn2 > 0.0) ? std::sqrt(w.h_ctrl->rr / w.h_ctrl->bn2) : 0.0;
   return HF_OK;
@@ -229,6 +232,7 @@ int hf_pcg_prepare_from_r(hf_ctx* c) {
   PcgWork& w = c->ws;
   k_pcg_rr0<<<w.grid, HF_BLOCK, 0, c->stream>>>(c->Npad, w.r.p, w.ctrl.p, 1);
   k_pcg_ctrl_init<<<1, HF_BLOCK, 0, c->stream>>>(w.ctrl.p, w.grid, c->rtol);
+  c->stat_launches += 2;
   HF_CUDA(cudaGetLastError());
   return HF_OK;
 }
@@ -237,6 +241,7 @@ int hf_pcg_prepare_from_r(hf_ctx* c) {
 int hf_pcg_prepare(hf_ctx* c) {
   PcgWork& w = c->ws;
   k_pcg_ctrl_init<<<1, HF_BLOCK, 0, c->stream>>>(w.ctrl.p, w.grid, c->rtol);
+  c->stat_launches += 1;
   HF_CUDA(cudaGetLastError());
   return HF_OK;
 }

@@ -160,6 +160,12 @@ class HeatSolver:
         _lib.check(self._L.hf_sample(self._h, len(nodes), _lib.ptr(nodes), _lib.ptr(out)))
         return out
 
+    def stats(self):
+        """dict: device ms of the last run loop, kernels launched, PCG iterations, last relres."""
+        st = np.zeros(4)
+        _lib.check(self._L.hf_get_stats(self._h, _lib.ptr(st)))
+        return {"run_ms": st[0], "launches": int(st[1]), "iterations": int(st[2]), "relres": st[3]}
+
     def project_gradient(self):
         g = np.empty((self.n, 2))
         it = C.c_int32()

@@ -106,6 +106,12 @@ int hf_run(hf_ctx* ctx, int32_t n_steps, const double* amp, double t_ic, double 
 
 int hf_sample(hf_ctx* ctx, int32_t n, const int32_t* nodes, double* out);
 
+/* Counters for benchmarking: stats[0] = device time of the step loop of the last hf_run /
+ * hf_ens_run in ms (CUDA events on the context stream), stats[1] = kernels launched since
+ * hf_create (graph kernel nodes included), stats[2] = PCG iterations since hf_create,
+ * stats[3] = relative residual of the last solve. */
+int hf_get_stats(hf_ctx* ctx, double* stats4);
+
 /* r-weighted L2 projection of grad(u_n) onto vector P1, grad[N,2] = (d/dz, d/dr)
  * (reference: run_no_diamond.py:471-491, :544-550). */
 int hf_project_gradient(hf_ctx* ctx, double* grad, int32_t* iters_out);
