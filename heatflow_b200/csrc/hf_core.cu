@@ -1,6 +1,7 @@
 // heatflow_b200 - context, mesh/dof-map/sparsity, P1 assembly, time step, C-ABI (sm_100a).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -409,6 +410,7 @@ extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
   HF_TRY(cell_coefs(c, 1.0, dt));
   HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valA0.p));
   HF_TRY(hf_build_sell(c, c->valA0, true, c->opA, &c->valA));
+  HF_TRY(hf_persist_plan(c, c->opA));
   c->valM1.release();
   c->op_built = true;
   c->proj_built = false;
@@ -576,8 +578,38 @@ __global__ void k_sample(int n, const int* __restrict__ nodes, const double* __r
   if (i < n) out[i] = u[nodes[i]];
 }
 
-static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double coeff, int* iters, double* relres) {
+// 0 = streaming graph chunks (host polls), 1 = persistent single-launch kernel
+static int pick_persist(hf_ctx* c, const SellOp& op, bool* persist) {
+  if (c->mode == 2 && !op.p_spw)
+    return hf_fail(HF_ERR_STATE, "solver mode 2 (persistent kernel) requested but the mesh does not fit on chip");
+  *persist = (c->mode == 2) || (c->mode == 0 && op.p_spw != 0);
+  return HF_OK;
+}
+
+// Synchronous completion of a persistent solve: read the control-block header.
+static int finish_sync(hf_ctx* c, int* iters, double* relres) {
+  PcgWork& w = c->ws;
+  HF_CUDA(cudaMemcpyAsync(w.h_ctrl, w.ctrl.p, sizeof(double) * 3 + sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  c->last_iters = w.h_ctrl->itA;
+  c->stat_iters += w.h_ctrl->itA;
+  c->stat_relres = (w.h_ctrl->bn2 > 0.0) ? std::sqrt(w.h_ctrl->rr / w.h_ctrl->bn2) : 0.0;
+  if (iters) *iters = w.h_ctrl->itA;
+  if (relres) *relres = c->stat_relres;
+  if (!w.h_ctrl->done) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "PCG did not converge in %d iterations (relres %.3e)", w.h_ctrl->itA, c->stat_relres);
+    return hf_fail(HF_ERR_NOCONV, msg);
+  }
+  return HF_OK;
+}
+
+// step_slot >= 0: fully asynchronous (persistent kernel only), iteration count goes to ws.step_iters[step_slot]
+static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double coeff, int* iters, double* relres,
+                       int step_slot) {
   if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_step: operator not built");
+  bool persist = false;
+  HF_TRY(pick_persist(c, c->opA, &persist));
   c->stat_launches += 2 + ((use_gauss && c->n_gauss) ? 1 : 0);
   if (use_gauss && c->n_gauss)
     k_bc_gauss<<<(c->n_gauss + 255) / 256, 256, 0, c->stream>>>(c->n_gauss, c->gauss_dof.p, c->gauss_r.p, amp, t_ic, coeff,
@@ -590,7 +622,12 @@ static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double
                                                   w.r.p, w.ctrl.p);
   HF_CUDA(cudaGetLastError());
   HF_TRY(hf_pcg_prepare(c));
-  HF_TRY(hf_pcg_solve(c, c->opA, iters, relres));
+  if (persist) {
+    HF_TRY(hf_pcg_solve_async(c, c->opA, step_slot));
+    if (step_slot < 0) HF_TRY(finish_sync(c, iters, relres));
+  } else {
+    HF_TRY(hf_pcg_solve(c, c->opA, iters, relres));
+  }
   k_step_finalize<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, w.x.p, c->opA.scale.p, c->u.p, c->uprev.p);
   HF_CUDA(cudaGetLastError());
   c->have_prev = true;
@@ -601,7 +638,7 @@ extern "C" int hf_step(hf_ctx* c, int32_t use_gauss, double amp, double t_ic, do
                        double* relres_out) {
   if (!c) return hf_fail(HF_ERR_ARG, "null context");
   cudaSetDevice(c->device);
-  HF_TRY(step_device(c, use_gauss, amp, t_ic, coeff, iters_out, relres_out));
+  HF_TRY(step_device(c, use_gauss, amp, t_ic, coeff, iters_out, relres_out, -1));
   HF_CUDA(cudaStreamSynchronize(c->stream));
   return HF_OK;
 }
@@ -617,11 +654,19 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
     HF_TRY(c->watch.upload(watch_nodes, n_watch, c->stream));
     if (c->hist.n < (size_t)n_steps * n_watch) HF_TRY(c->hist.alloc((size_t)n_steps * n_watch, c->stream));
   }
+  bool persist = false;
+  HF_TRY(pick_persist(c, c->opA, &persist));
+  PcgWork& w = c->ws;
+  if (persist) {
+    if (w.step_iters.n < (size_t)n_steps) HF_TRY(w.step_iters.alloc(n_steps, c->stream));
+    HF_CUDA(cudaMemsetAsync(w.fail.p, 0, sizeof(int), c->stream));
+  }
   HF_CUDA(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < n_steps; ++s) {
     int it = 0;
-    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr));
-    if (iters) iters[s] = it;
+    // XDMF field output needs the state on the host after every step; the copy is stream ordered
+    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr, persist ? s : -1));
+    if (iters && !persist) iters[s] = it;
     if (n_watch) c->stat_launches += 1;
     if (n_watch)
       k_sample<<<(n_watch + 255) / 256, 256, 0, c->stream>>>(n_watch, c->watch.p, c->u.p, c->hist.p + (size_t)s * n_watch);
@@ -635,6 +680,19 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
   float ms = 0.f;
   HF_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->stat_run_ms = ms;
+  if (persist && n_steps) {
+    std::vector<int> hit(n_steps);
+    int nfail = 0;
+    HF_TRY(w.step_iters.download(hit.data(), n_steps, c->stream));
+    HF_TRY(w.fail.download(&nfail, 1, c->stream));
+    for (int s = 0; s < n_steps; ++s) {
+      if (iters) iters[s] = hit[s];
+      c->stat_iters += hit[s];
+    }
+    c->last_iters = hit[n_steps - 1];
+    if (nfail) return hf_fail(HF_ERR_NOCONV, "PCG hit the iteration cap in " + std::to_string(nfail) + " of " +
+                                                 std::to_string(n_steps) + " time steps");
+  }
   return HF_OK;
 }
 
@@ -754,6 +812,7 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 0.0, c->ck.p);
     HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, 1, vals.p));
     HF_TRY(hf_build_sell(c, vals, false, c->opMr, nullptr));
+    HF_TRY(hf_persist_plan(c, c->opMr));
     HF_TRY(c->proj_b.alloc((size_t)2 * c->Npad, c->stream));
     HF_TRY(c->proj_g.alloc((size_t)2 * c->N, c->stream));
     c->proj_built = true;
@@ -772,7 +831,15 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     HF_TRY(hf_pcg_prepare_from_r(c));
     int it = 0;
     c->last_iters = 40;
-    HF_TRY(hf_pcg_solve(c, c->opMr, &it, nullptr));
+    bool persist = false;
+    HF_TRY(pick_persist(c, c->opMr, &persist));
+    if (persist) {
+      HF_TRY(hf_pcg_solve_async(c, c->opMr, -1));
+      HF_TRY(finish_sync(c, &it, nullptr));
+    } else {
+      HF_TRY(hf_pcg_solve(c, c->opMr, &it, nullptr));
+    }
+    if (getenv("HF_DEBUG")) fprintf(stderr, "[hf] projection comp %d: %d iterations, relres %.3e\n", comp, it, c->stat_relres);
     total += it;
     k_store_comp<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, w.x.p, c->opMr.scale.p, comp, c->proj_g.p);
   }

@@ -95,6 +95,10 @@ struct SellOp {
   DevBuf<double> val;
   DevBuf<double> scale;                // s_i = sqrt(diag) (1 on Dirichlet rows)
   mutable cudaGraphExec_t chunk_exec[3] = {nullptr, nullptr, nullptr};   // captured PCG iteration chunks
+  // plan of the persistent (single-launch) PCG kernel; spw == 0 => not eligible
+  int p_spw = 0, p_grid = 0, p_mat_cap = 0, p_sz_cap = 0;
+  size_t p_smem = 0;
+  DevBuf<int2> p_range;                // per CTA: [lo, hi) column range of its rows
   SellView view() const { return SellView{nslices, slice_ptr.p, col.p, val.p}; }
   void drop_graphs() const {
     for (auto& g : chunk_exec) {
@@ -108,6 +112,11 @@ struct SellOp {
 struct PcgWork {
   DevBuf<double> x, r, p0, p1, q;
   DevBuf<HfCtrl> ctrl;
+  DevBuf<uint4> slots;                 // flag-with-data reduction slots (persistent kernel)
+  DevBuf<uint4> qpk;                   // [2][Npad] q = A p exchange packets (persistent kernel)
+  DevBuf<unsigned> gen;                // barrier generation, monotonic across launches
+  DevBuf<int> step_iters;              // per-step iteration counts written by the persistent kernel
+  DevBuf<int> fail;                    // number of solves that hit max_iters
   HfCtrl* h_ctrl = nullptr;            // pinned mirror of the control-block header
   int grid = 0;
 };
@@ -207,6 +216,8 @@ __device__ __forceinline__ int hf_ld_stream(const int* p) {
 // shared between translation units
 int hf_pcg_alloc(hf_ctx* c);
 int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out);
+int hf_persist_plan(hf_ctx* c, SellOp& op);
+int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot);
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out);
 int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out);
 void hf_ens_free(hf_ctx* c);

@@ -132,10 +132,11 @@ k_pcg_rr0(int n, const double* __restrict__ r, HfCtrl* __restrict__ c, int bn_fr
 __global__ void __launch_bounds__(HF_BLOCK) k_pcg_ctrl_init(HfCtrl* c, int nparts, double rtol) {
   __shared__ double sh[HF_BLOCK / 32];
   const double bn2 = hf_sum_parts(c->part_bn, nparts, sh);
+  const double rr0 = hf_sum_parts(c->part_rr[0], nparts, sh);
   if (threadIdx.x == 0) {
     c->bn2 = bn2;
     c->thr = rtol * rtol * bn2;
-    c->rr = 0.0;
+    c->rr = rr0;
     c->done = 0;
     c->itA = 0;
     c->itB = 0;

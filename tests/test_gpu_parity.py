@@ -87,10 +87,11 @@ def test_rhs_and_single_step(small_nd):
     s.close()
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
 @pytest.mark.parametrize("name", ["geballe_no_diamond", "geballe_with_diamond"])
-def test_history_every_step(name):
+def test_history_every_step(name, mode):
     c = build_case(name, 8.0)
-    s = make_solver(c)
+    s = make_solver(c, mode=mode)
     O = make_oracle(c)
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.9e-6, 0.0)])
     hist, iters, fields = s.run(c.amps, c.ic, c.coeff, watch, keep_fields=True)
@@ -114,10 +115,11 @@ def test_constant_state_invariance(small_wd):
     s.close()
 
 
-def test_full_size_no_diamond_vs_oracle():
+@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+def test_full_size_no_diamond_vs_oracle(mode):
     # configs[1] at the cfg's own mesh sizes (~1.1e5 dofs, 40 steps)
     c = build_case("geballe_no_diamond", 1.0)
-    s = make_solver(c)
+    s = make_solver(c, mode=mode)
     O = make_oracle(c)
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
     hist, iters, _ = s.run(c.amps, c.ic, c.coeff, watch)
@@ -127,11 +129,12 @@ def test_full_size_no_diamond_vs_oracle():
     s.close()
 
 
-def test_run_is_bit_reproducible(small_nd):
+@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+def test_run_is_bit_reproducible(small_nd, mode):
     c = small_nd
     out = []
     for _ in range(2):
-        s = make_solver(c)
+        s = make_solver(c, mode=mode)
         hist, iters, _ = s.run(c.amps[:25], c.ic, c.coeff, [5, 50])
         out.append((hist, iters, s.get_state()))
         s.close()

@@ -25,7 +25,8 @@ def probe(name, scale, warm=0.0, mode=0, steps=None):
     s.close()
 
 if __name__ == "__main__":
-    probe("geballe_no_diamond", 1.0)
-    probe("geballe_with_diamond", 1.0)
-    probe("geballe_with_diamond", 1.0, warm=1.0)
-    probe("geballe_with_diamond", 0.35, steps=10)
+    for mode in (1, 2):
+        probe("geballe_no_diamond", 1.0, mode=mode)
+        probe("geballe_with_diamond", 1.0, mode=mode)
+    probe("geballe_with_diamond", 1.0, warm=1.0, mode=2)
+    probe("geballe_with_diamond", 0.7, mode=0, steps=30)
