@@ -1,0 +1,168 @@
+"""GPU tests of the reference-facing entry points: files written, values against the oracle."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import yaml
+
+from helpers import build_case, load_cfg, make_solver
+from oracle import heat_oracle as ho
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def coarse_cfg(name, factor=8.0):
+    cfg = load_cfg(name)
+    for m in cfg["mats"].values():
+        m["mesh"] = float(m["mesh"]) * factor
+    return cfg
+
+
+def sweep_watchers(cfg):
+    import parameter_sweep
+    return parameter_sweep.get_watcher_points(cfg)
+
+
+def oracle_for(cfg, mesh_folder, with_diamond):
+    """Oracle on the mesh the runner wrote to disk."""
+    from heatflow_b200 import problem
+    from heatflow_b200.mesh_and_materials import read_msh
+    nodes, tris, tag, _ = read_msh(os.path.join(mesh_folder, "mesh.msh"))
+    mats, _, info = (problem.stack_with_diamond if with_diamond else problem.stack_no_diamond)(cfg)
+    kap = np.array([m.properties["k"] for m in mats])[tag - 1]
+    rc = np.array([m.properties["rho_cv"] for m in mats])[tag - 1]
+    S = int(cfg["timing"]["num_steps"])
+    dt = float(cfg["timing"]["t_final"]) / S
+    ht, hT = ho.load_heating(cfg["heating"]["file"])
+    zc = next(m for m in mats if m.name == "p_coupler").boundaries[0]
+    bcs = [(ho.locate_row_dofs(nodes, "left"), "const"), (ho.locate_row_dofs(nodes, "right"), "const"),
+           (ho.locate_row_dofs(nodes, "top"), "const"),
+           (ho.locate_row_dofs(nodes, "x", coord=zc, length=2 * info["r_sample"], center=0.0), "gauss")]
+    O = ho.Oracle2D(nodes, tris, rc, kap, dt, bcs, float(cfg["heating"]["ic_temp"]), float(cfg["heating"]["fwhm"]), ht, hT)
+    return O, nodes, tris, S, dt
+
+
+def test_run_with_diamond_outputs(tmp_path):
+    import run_with_diamond
+    cfg = coarse_cfg("geballe_with_diamond")
+    wp = sweep_watchers(cfg)
+    mesh_folder, out = str(tmp_path / "mesh"), str(tmp_path / "out")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ret = run_with_diamond.run_simulation(cfg, mesh_folder, rebuild_mesh=True, output_folder=out, watcher_points=wp,
+                                              write_xdmf=True)
+    assert ret is None
+    assert "Simulation progress: 100% (step 100/100)" in buf.getvalue() and "--- Timing Summary ---" in buf.getvalue()
+    assert sorted(os.listdir(out)) == ["output.xdmf", "output_data", "used_config.yaml", "watcher_points.csv"]
+    assert yaml.safe_load(open(os.path.join(out, "used_config.yaml"))) == cfg
+    df = pd.read_csv(os.path.join(out, "watcher_points.csv"))
+    assert list(df.columns) == ["time", "pside", "oside"] and len(df) == 100
+    O, nodes, tris, S, dt = oracle_for(cfg, mesh_folder, True)
+    watch = ho.nearest_nodes(nodes, list(wp.values()))
+    hist, fields = O.run(S, watch, keep_fields=True)
+    assert np.allclose(df["time"], (np.arange(S) + 1) * dt, rtol=1e-15)
+    assert np.abs(df[["pside", "oside"]].to_numpy() / hist - 1).max() <= 1e-10
+    # XDMF: t = 0 field + one per step, readable with the extract helper
+    from io_utilities.xdmf_extract import extract_point_timeseries_xdmf
+    times, data = extract_point_timeseries_xdmf(os.path.join(out, "output.xdmf"), "Temperature (K)",
+                                                [tuple(nodes[watch[0]]), tuple(nodes[watch[1]])])
+    assert len(times) == S + 1 and times[0] == 0.0 and np.all(data[:, 0] == 300.0)
+    assert np.abs(data[:, 1:].T / hist - 1).max() <= 1e-10
+    # reusing the mesh (rebuild_mesh=False) and the list form of watcher_points, no XDMF
+    out2 = str(tmp_path / "out2")
+    run_with_diamond.run_simulation(cfg, mesh_folder, rebuild_mesh=False, output_folder=out2,
+                                    watcher_points=[{"name": k, "coords": v} for k, v in wp.items()],
+                                    write_xdmf=False, suppress_print=True)
+    assert sorted(os.listdir(out2)) == ["used_config.yaml", "watcher_points.csv"]
+    assert pd.read_csv(os.path.join(out2, "watcher_points.csv")).equals(df)
+    with pytest.raises(ValueError):
+        run_with_diamond.run_simulation(cfg, mesh_folder, watcher_points="pside", output_folder=out2, write_xdmf=False,
+                                        suppress_print=True)
+
+
+def test_run_no_diamond_gradient_outputs_and_1d(tmp_path):
+    import run_no_diamond
+    import run_no_diamond_1d
+    cfg = coarse_cfg("geballe_no_diamond", 4.0)
+    wp = sweep_watchers(cfg)
+    mesh_folder, out = str(tmp_path / "mesh"), str(tmp_path / "out")
+    run_no_diamond.run_simulation(cfg, mesh_folder, rebuild_mesh=True, output_folder=out, watcher_points=wp,
+                                  write_xdmf=False, suppress_print=True)
+    assert sorted(os.listdir(out)) == ["radial_gradient.csv", "radial_gradient_raw.csv", "used_config.yaml", "watcher_points.csv"]
+    O, nodes, tris, S, dt = oracle_for(cfg, mesh_folder, False)
+    watch = ho.nearest_nodes(nodes, list(wp.values()))
+    P = ho.GradientProjector(nodes, tris)
+    centres, groups = ho.radial_bins(nodes)
+    axis, axis_z = ho.axis_nodes(nodes)
+    hist, rows, raw = [], [], []
+    for s in range(S):
+        u = O.step((s + 1) * dt)
+        hist.append(u[watch])
+        g = P.project(u)[:, 1]
+        rows.append([g[idx].mean() for idx in groups])
+        raw.append(g[axis])
+    df = pd.read_csv(os.path.join(out, "watcher_points.csv"))
+    assert np.abs(df[["pside", "oside"]].to_numpy() / np.array(hist) - 1).max() <= 1e-10
+    gd = pd.read_csv(os.path.join(out, "radial_gradient.csv"), index_col=0)
+    assert gd.index.name == "time" and np.allclose(gd.columns.values.astype(float), centres, rtol=1e-14)
+    scale = np.abs(np.array(rows)).max()
+    assert np.abs(gd.values - np.array(rows)).max() <= 1e-8 * scale
+    gr = pd.read_csv(os.path.join(out, "radial_gradient_raw.csv"), index_col=0)
+    assert np.allclose(gr.columns.values.astype(float), axis_z, rtol=1e-14)
+    assert np.abs(gr.values - np.array(raw)).max() <= 1e-8 * np.abs(np.array(raw)).max()
+
+    # ---- 1-D runner on the axis of the same mesh, with and without the radial correction
+    z, cells, tags, verts = ho.extract_axis_submesh(nodes, tris, ho.np.asarray(
+        __import__("heatflow_b200.mesh_and_materials", fromlist=["read_msh"]).read_msh(os.path.join(mesh_folder, "mesh.msh"))[2]))
+    from heatflow_b200 import problem
+    mats, _, _ = problem.stack_no_diamond(cfg)
+    kap_t = np.array([m.properties["k"] for m in mats])
+    rc_t = np.array([m.properties["rho_cv"] for m in mats])
+    zmin = mats[0].boundaries[0]
+    heat_z = zmin + float(cfg["mats"]["p_ins"]["z"])
+    heat = ho.locate_row_dofs(np.column_stack((z, np.zeros_like(z))), "x", coord=heat_z)
+    ht, hT = ho.load_heating(cfg["heating"]["file"])
+    for corr in (False, True):
+        out1 = str(tmp_path / f"out1d_{corr}")
+        dom1, tags1, maps = run_no_diamond_1d.run_1d(cfg, mesh_folder, output_folder=out1, watcher_points=wp, write_xdmf=corr,
+                                                     suppress_print=True, use_radial_correction=corr,
+                                                     radial_gradient_path=os.path.join(out, "radial_gradient.csv"))
+        assert np.array_equal(dom1.geometry.x[:, 0], z) and np.array_equal(tags1.values, tags)
+        O1 = ho.Oracle1D(z, cells, rc_t[tags - 1], kap_t[tags - 1], dt, [([0], "const"), ([len(z) - 1], "const"), (heat, "heat")],
+                         300.0, ht, hT)
+        from scipy.interpolate import RegularGridInterpolator
+        interp = RegularGridInterpolator((gd.index.values.astype(float), gd.columns.values.astype(float)), gd.values)
+        kap_cell = kap_t[tags - 1]
+        zlo, zhi = z[cells[:, 0]], z[cells[:, 1]]
+        node_k = np.array([kap_cell[tags[np.flatnonzero((zlo <= zc) & (zc <= zhi))[0]]] for zc in z])   # reference quirk
+        w1 = [int(np.argmin(np.abs(z - p[0]))) for p in wp.values()]
+        want = []
+        for s in range(S):
+            t = (s + 1) * dt
+            src = None
+            if corr:
+                zc = np.clip(z, gd.columns.values.astype(float).min(), gd.columns.values.astype(float).max())
+                gv = interp(np.column_stack([np.full_like(zc, np.clip(t, gd.index.min(), gd.index.max())), zc]))
+                gv[z != zc] *= 0.1
+                src = 2.0 * node_k * gv / 0.1e-6
+            want.append(O1.step(t, source=src)[w1])
+        got = pd.read_csv(os.path.join(out1, "watcher_points.csv"))[["pside", "oside"]].to_numpy()
+        assert np.abs(got / np.array(want) - 1).max() <= 1e-10, corr
+
+
+@pytest.mark.parametrize("name,cfg", [("no_diamond_s16", "geballe_no_diamond"), ("with_diamond_s16", "geballe_with_diamond")])
+def test_gpu_reproduces_golden_fixture(name, cfg):
+    gold = np.load(os.path.join(HERE, "golden", f"{name}.npz"))
+    c = build_case(cfg, float(gold["size_scale"]))
+    s = make_solver(c)
+    rowptr, col = s.csr(values=False)
+    assert np.array_equal(rowptr, gold["rowptr"]) and np.array_equal(col, gold["col"])
+    hist, iters, fields = s.run(c.amps, c.ic, c.coeff, gold["watch"], keep_fields=True)
+    assert np.abs(hist / gold["hist"] - 1).max() <= 1e-10
+    for k, f in zip(gold["field_steps"], gold["fields"]):
+        assert np.abs(fields[int(k)] / f - 1).max() <= 1e-10
+    s.close()
