@@ -25,6 +25,7 @@ SIGNATURES = {
     "hf_device_count": (C.c_int, []),
     "hf_create": (_vp, [C.c_int]),
     "hf_destroy": (None, [_vp]),
+    "hf_set_ordering": (C.c_int, [_vp, _i32]),
     "hf_set_mesh": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hf_set_materials": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "hf_set_bcs": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _vp]),

@@ -69,21 +69,137 @@ extern "C" void hf_destroy(hf_ctx* c) {
   cudaStreamDestroy(s);
 }
 
+// Position of (x, y) in [0, 65535]^2 along the Hilbert curve.
+static uint64_t hilbert_key(uint32_t x, uint32_t y) {
+  const uint32_t n = 65536u;
+  uint64_t d = 0;
+  for (uint32_t s = n / 2; s > 0; s /= 2) {
+    const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+    d += (uint64_t)s * s * ((3u * rx) ^ ry);
+    if (ry == 0) {
+      if (rx == 1) {
+        x = n - 1 - x;
+        y = n - 1 - y;
+      }
+      std::swap(x, y);
+    }
+  }
+  return d;
+}
+
+extern "C" int hf_set_ordering(hf_ctx* c, int32_t ordering) {
+  if (!c || ordering < 0 || ordering > 2) return hf_fail(HF_ERR_ARG, "hf_set_ordering: ordering must be 0 (auto), 1 (as given) or 2 (Hilbert)");
+  c->ordering_req = ordering;
+  return HF_OK;
+}
+
+__global__ void k_gather_nodal(int n, int ncomp, const int* __restrict__ idx, const double* __restrict__ src,
+                               double* __restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * ncomp) {
+    const int i = t / ncomp, a = t - i * ncomp;
+    dst[t] = src[(size_t)idx[i] * ncomp + a];
+  }
+}
+
+// host array in the caller's node numbering -> device array in internal numbering
+int hf_upload_nodal(hf_ctx* c, const double* h_user, double* d_internal) {
+  if (!c->permuted) {
+    HF_CUDA(cudaMemcpyAsync(d_internal, h_user, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    HF_CUDA(cudaMemcpyAsync(c->stage.p, h_user, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
+    k_gather_nodal<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, 1, c->order_d.p, c->stage.p, d_internal);
+    HF_CUDA(cudaGetLastError());
+  }
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return HF_OK;
+}
+
+// device array [N, ncomp] in internal numbering -> host array in the caller's numbering (ncomp <= 2)
+int hf_download_nodal(hf_ctx* c, const double* d_internal, double* h_user, int ncomp) {
+  const double* src = d_internal;
+  if (c->permuted) {
+    k_gather_nodal<<<(c->N * ncomp + 255) / 256, 256, 0, c->stream>>>(c->N, ncomp, c->rank_d.p, d_internal, c->stage.p);
+    HF_CUDA(cudaGetLastError());
+    src = c->stage.p;
+  }
+  HF_CUDA(cudaMemcpyAsync(h_user, src, sizeof(double) * c->N * ncomp, cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return HF_OK;
+}
+
+int hf_internal_nodes(hf_ctx* c, int n, const int32_t* user_nodes, std::vector<int>& out) {
+  out.resize(n);
+  for (int i = 0; i < n; ++i) {
+    if (user_nodes[i] < 0 || user_nodes[i] >= c->N) return hf_fail(HF_ERR_ARG, "node index out of range");
+    out[i] = c->permuted ? c->h_rank[user_nodes[i]] : user_nodes[i];
+  }
+  return HF_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // mesh -> dof map, node->cell adjacency, CSR sparsity pattern (host, integer work, one-off)
 // ---------------------------------------------------------------------------------------
-extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const double* xy,
-                           const int32_t* cells, const int32_t* cell_tag) {
-  if (!c || !xy || !cells || !cell_tag) return hf_fail(HF_ERR_ARG, "hf_set_mesh: null argument");
+extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const double* xy_user,
+                           const int32_t* cells_user, const int32_t* cell_tag) {
+  if (!c || !xy_user || !cells_user || !cell_tag) return hf_fail(HF_ERR_ARG, "hf_set_mesh: null argument");
   if (N <= 0 || E <= 0 || (nv != 2 && nv != 3)) return hf_fail(HF_ERR_ARG, "hf_set_mesh: need N > 0, E > 0, nv in {2,3}");
   for (int64_t k = 0; k < (int64_t)E * nv; ++k)
-    if (cells[k] < 0 || cells[k] >= N) return hf_fail(HF_ERR_ARG, "hf_set_mesh: cell references a node outside [0, N)");
+    if (cells_user[k] < 0 || cells_user[k] >= N) return hf_fail(HF_ERR_ARG, "hf_set_mesh: cell references a node outside [0, N)");
   cudaSetDevice(c->device);
+  hf_ens_free(c);
   c->N = N;
   c->E = E;
   c->nv = nv;
   c->Npad = (N + HF_SLICE - 1) / HF_SLICE * HF_SLICE;
   c->op_built = c->proj_built = false;
+  // ---- internal numbering.  auto: meshes small enough for the on-chip persistent kernel keep the
+  // caller's (banded) order, which that kernel's contiguous ghost ranges rely on; larger meshes are
+  // sorted along a Hilbert curve so that consecutive rows form compact 2-D patches.
+  int ordering = c->ordering_req;
+  if (ordering == 0) ordering = (nv == 3 && c->Npad > c->sm_count * 1024) ? 2 : 1;
+  if (nv != 3) ordering = 1;
+  c->permuted = (ordering == 2);
+  c->h_rank.clear();
+  c->h_order.clear();
+  std::vector<double> xy_store;
+  std::vector<int> cells_store;
+  const double* xy = xy_user;
+  const int32_t* cells = cells_user;
+  if (c->permuted) {
+    double lo[2] = {xy_user[0], xy_user[1]}, hi[2] = {xy_user[0], xy_user[1]};
+    for (int i = 0; i < N; ++i)
+      for (int a = 0; a < 2; ++a) {
+        lo[a] = std::min(lo[a], xy_user[2 * i + a]);
+        hi[a] = std::max(hi[a], xy_user[2 * i + a]);
+      }
+    const double span = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), 1e-300);
+    std::vector<std::pair<uint64_t, int>> keyed(N);
+    for (int i = 0; i < N; ++i) {
+      const uint32_t qx = (uint32_t)std::min(65535.0, std::max(0.0, (xy_user[2 * i] - lo[0]) / span * 65535.0));
+      const uint32_t qy = (uint32_t)std::min(65535.0, std::max(0.0, (xy_user[2 * i + 1] - lo[1]) / span * 65535.0));
+      keyed[i] = std::make_pair(hilbert_key(qx, qy), i);
+    }
+    std::sort(keyed.begin(), keyed.end());
+    c->h_order.resize(N);
+    c->h_rank.resize(N);
+    for (int n = 0; n < N; ++n) {
+      c->h_order[n] = keyed[n].second;
+      c->h_rank[keyed[n].second] = n;
+    }
+    xy_store.resize((size_t)N * 2);
+    for (int n = 0; n < N; ++n) {
+      xy_store[2 * n] = xy_user[2 * c->h_order[n]];
+      xy_store[2 * n + 1] = xy_user[2 * c->h_order[n] + 1];
+    }
+    cells_store.resize((size_t)E * nv);
+    for (int64_t k = 0; k < (int64_t)E * nv; ++k) cells_store[k] = c->h_rank[cells_user[k]];
+    xy = xy_store.data();
+    cells = cells_store.data();
+    HF_TRY(c->rank_d.upload(c->h_rank.data(), N, c->stream));
+    HF_TRY(c->order_d.upload(c->h_order.data(), N, c->stream));
+  }
+  HF_TRY(c->stage.alloc((size_t)2 * N, c->stream));
   // node -> cells, ascending cell index (fixes the summation order of the gather assembly)
   std::vector<int> ptr(N + 1, 0);
   for (int64_t k = 0; k < (int64_t)E * nv; ++k) ptr[cells[k] + 1]++;
@@ -125,7 +241,7 @@ extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const do
   c->have_prev = c->have_source = false;
   c->n_bc = c->n_gauss = 0;
   HF_TRY(hf_pcg_alloc(c));
-  HF_CUDA(cudaStreamSynchronize(c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));   // the staging vectors above go out of scope here
   return HF_OK;
 }
 
@@ -156,17 +272,19 @@ extern "C" int hf_set_bcs(hf_ctx* c, int32_t n_bc, const int32_t* bc_dofs, const
     if (bc_dofs[i] < 0 || bc_dofs[i] >= c->N) return hf_fail(HF_ERR_ARG, "hf_set_bcs: dof out of range");
     if (i && bc_dofs[i] <= bc_dofs[i - 1]) return hf_fail(HF_ERR_ARG, "hf_set_bcs: bc_dofs must be sorted and unique");
   }
-  std::vector<int> gd(n_gauss);
+  std::vector<int> bd, gd(n_gauss);   // internal numbering (slot order unchanged)
+  HF_TRY(hf_internal_nodes(c, n_bc, bc_dofs, bd));
   for (int i = 0; i < n_gauss; ++i) {
     if (gauss_slot[i] < 0 || gauss_slot[i] >= n_bc) return hf_fail(HF_ERR_ARG, "hf_set_bcs: gauss_slot out of range");
-    gd[i] = bc_dofs[gauss_slot[i]];
+    gd[i] = bd[gauss_slot[i]];
   }
   cudaSetDevice(c->device);
+  hf_ens_free(c);
   c->n_bc = n_bc;
   c->n_gauss = n_gauss;
   HF_CUDA(cudaMemsetAsync(c->bcflag.p, 0, c->Npad, c->stream));
   HF_CUDA(cudaMemsetAsync(c->gfull.p, 0, sizeof(double) * c->Npad, c->stream));
-  HF_TRY(c->bc_dofs.upload(bc_dofs, n_bc, c->stream));
+  HF_TRY(c->bc_dofs.upload(bd.data(), n_bc, c->stream));
   HF_TRY(c->gauss_dof.upload(gd.data(), n_gauss, c->stream));
   HF_TRY(c->gauss_r.upload(gauss_r, n_gauss, c->stream));
   if (n_bc) {
@@ -316,10 +434,11 @@ __global__ void k_diag_scale(int N, int Npad, const int* __restrict__ rowptr, co
   scale[i] = s;
 }
 
-__global__ void k_fill_sell(int N, int Npad, const int* __restrict__ rowptr, const int* __restrict__ col,
+__global__ void k_fill_sell(int N, int Npad, int R, const int* __restrict__ rowptr, const int* __restrict__ col,
                             const double* __restrict__ val, const unsigned char* __restrict__ bcflag,
                             int apply_bc, const double* __restrict__ scale, const int* __restrict__ slice_ptr,
-                            int* __restrict__ scol, double* __restrict__ sval, double* __restrict__ val_bc) {
+                            const unsigned short* __restrict__ lcol_csr, int* __restrict__ scol,
+                            unsigned short* __restrict__ slcol, double* __restrict__ sval, double* __restrict__ val_bc) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Npad) return;
   const int s = i / HF_SLICE, lane = i % HF_SLICE;
@@ -334,17 +453,58 @@ __global__ void k_fill_sell(int N, int Npad, const int* __restrict__ rowptr, con
   const double si = scale[i];
   for (int k = 0; k < w; ++k) {
     int cj = i;
+    unsigned short lc = (unsigned short)(i % R);   // padding entries point at the row itself, value 0
     double v = 0.0;
     if (k < len) {
       cj = col[r0 + k];
+      lc = lcol_csr[r0 + k];
       double a = val[r0 + k];
       if (apply_bc && (bci || bcflag[cj])) a = (cj == i) ? 1.0 : 0.0;
       if (val_bc) val_bc[r0 + k] = a;
       v = a / (si * scale[cj]);
     }
     scol[base + k * HF_SLICE + lane] = cj;
+    slcol[base + k * HF_SLICE + lane] = lc;
     sval[base + k * HF_SLICE + lane] = v;
   }
+}
+
+// Chunks of R consecutive rows -> halo lists (columns outside the chunk, ascending) and 16-bit
+// local column indices in CSR slot order.  Host, integer work, once per mesh and R.
+int hf_build_patches(const hf_ctx* c, int R, std::vector<int>& halo_ptr, std::vector<int>& halo_idx,
+                     std::vector<unsigned short>& lcol, int* halo_max) {
+  const int N = c->N;
+  const int nchunks = (c->Npad + R - 1) / R;
+  halo_ptr.assign(nchunks + 1, 0);
+  halo_idx.clear();
+  lcol.resize(c->nnz);
+  std::vector<int> slot(N, -1), touched;
+  *halo_max = 0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int lo = ch * R, hi = std::min(lo + R, N);
+    touched.clear();
+    for (int i = lo; i < hi; ++i)
+      for (int k = c->h_rowptr[i]; k < c->h_rowptr[i + 1]; ++k) {
+        const int j = c->h_col[k];
+        if ((j < lo || j >= lo + R) && slot[j] < 0) {
+          slot[j] = 0;
+          touched.push_back(j);
+        }
+      }
+    std::sort(touched.begin(), touched.end());
+    if (R + (int)touched.size() > 65535) return hf_fail(HF_ERR_ARG, "patch halo exceeds the 16-bit local column range");
+    for (size_t h = 0; h < touched.size(); ++h) slot[touched[h]] = (int)h;
+    for (int i = lo; i < hi; ++i)
+      for (int k = c->h_rowptr[i]; k < c->h_rowptr[i + 1]; ++k) {
+        const int j = c->h_col[k];
+        lcol[k] = (unsigned short)((j >= lo && j < lo + R) ? (j - lo) : (R + slot[j]));
+      }
+    for (int j : touched) slot[j] = -1;
+    halo_idx.insert(halo_idx.end(), touched.begin(), touched.end());
+    halo_ptr[ch + 1] = (int)halo_idx.size();
+    *halo_max = std::max(*halo_max, (int)touched.size());
+  }
+  return HF_OK;
 }
 
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out) {
@@ -360,8 +520,38 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   op.drop_graphs();
   op.nslices = nsl;
   op.padded_nnz = (size_t)sp[nsl];
+  // chunk size of the streaming kernel: one CTA per chunk, at least ~3 CTAs per SM when the mesh allows
+  op.R = (c->Npad >= 3 * c->sm_count * 1024) ? 1024 : (c->Npad >= 3 * c->sm_count * 512) ? 512 : 256;
+  if (const char* env = getenv("HF_CHUNK_R")) {   // tuning knob
+    const int r = atoi(env);
+    if (r == 256 || r == 512 || r == 1024) op.R = r;
+  }
+  op.nchunks = (c->Npad + op.R - 1) / op.R;
+  op.mat_cap = 0;
+  for (int ch = 0; ch < op.nchunks; ++ch) {
+    const int s0 = ch * (op.R / HF_SLICE), s1 = std::min(s0 + op.R / HF_SLICE, nsl);
+    op.mat_cap = std::max(op.mat_cap, sp[s1] - sp[s0]);
+  }
+  std::vector<int> hptr, hidx;
+  std::vector<unsigned short> lcol;
+  HF_TRY(hf_build_patches(c, op.R, hptr, hidx, lcol, &op.halo_max));
+  // operator block (values + 16-bit columns) + p (own + halo) + r (own)
+  op.iter_smem = (size_t)op.mat_cap * 10 + sizeof(double) * ((size_t)2 * op.R + op.halo_max);
+  {
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+    if (op.iter_smem + 1024 > (size_t)max_smem)
+      return hf_fail(HF_ERR_STATE, "streaming PCG chunk does not fit in shared memory (halo of " + std::to_string(op.halo_max) +
+                                       " rows); use hf_set_ordering(ctx, 2)");
+  }
+  DevBuf<unsigned short> lcol_csr;
+  HF_TRY(lcol_csr.upload(lcol.data(), lcol.size(), c->stream));
+  HF_TRY(op.halo_ptr.upload(hptr.data(), hptr.size(), c->stream));
+  if (hidx.empty()) hidx.push_back(0);
+  HF_TRY(op.halo_idx.upload(hidx.data(), hidx.size(), c->stream));
   HF_TRY(op.slice_ptr.upload(sp.data(), nsl + 1, c->stream));
   HF_TRY(op.col.alloc(op.padded_nnz, c->stream));
+  HF_TRY(op.lcol.alloc(op.padded_nnz, c->stream));
   HF_TRY(op.val.alloc(op.padded_nnz, c->stream));
   HF_TRY(op.scale.alloc(c->Npad, c->stream));
   if (val_bc_out) HF_TRY(val_bc_out->alloc(c->nnz, c->stream));
@@ -370,13 +560,15 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   const int g = (c->Npad + 255) / 256;
   k_diag_scale<<<g, 256, 0, c->stream>>>(c->N, c->Npad, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
                                          op.scale.p, bad.p);
-  k_fill_sell<<<g, 256, 0, c->stream>>>(c->N, c->Npad, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
-                                        op.scale.p, op.slice_ptr.p, op.col.p, op.val.p, val_bc_out ? val_bc_out->p : nullptr);
+  k_fill_sell<<<g, 256, 0, c->stream>>>(c->N, c->Npad, op.R, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
+                                        op.scale.p, op.slice_ptr.p, lcol_csr.p, op.col.p, op.lcol.p, op.val.p,
+                                        val_bc_out ? val_bc_out->p : nullptr);
   HF_CUDA(cudaGetLastError());
   int hbad = 0;
-  HF_TRY(bad.download(&hbad, 1, c->stream));
+  HF_TRY(bad.download(&hbad, 1, c->stream));   // also orders the kernels before lcol_csr is freed
   if (hbad) return hf_fail(HF_ERR_STATE, "operator has a non-positive diagonal at row " + std::to_string(hbad - 1) +
                                              " (unset material or degenerate cell?)");
+  if (c->ws.parts.n < (size_t)4 * op.nchunks) HF_TRY(c->ws.parts.alloc((size_t)4 * op.nchunks, c->stream));
   return HF_OK;
 }
 
@@ -426,16 +618,53 @@ extern "C" int hf_get_sizes(hf_ctx* c, int32_t* n_nodes, int64_t* nnz) {
   return HF_OK;
 }
 
+// CSR arrays in the caller's node numbering.  With an internal permutation the pattern is mapped
+// back row by row (columns re-sorted) and `slot` records where each entry lives internally.
+static void user_pattern(const hf_ctx* c, std::vector<int>& rowptr, std::vector<int>& col, std::vector<int>& slot) {
+  const int N = c->N;
+  rowptr.assign(N + 1, 0);
+  col.resize(c->nnz);
+  slot.resize(c->nnz);
+  for (int i = 0; i < N; ++i) {
+    const int ri = c->h_rank[i];
+    rowptr[i + 1] = rowptr[i] + (c->h_rowptr[ri + 1] - c->h_rowptr[ri]);
+  }
+  std::vector<std::pair<int, int>> tmp;
+  for (int i = 0; i < N; ++i) {
+    const int ri = c->h_rank[i];
+    tmp.clear();
+    for (int k = c->h_rowptr[ri]; k < c->h_rowptr[ri + 1]; ++k) tmp.emplace_back(c->h_order[c->h_col[k]], k);
+    std::sort(tmp.begin(), tmp.end());
+    for (size_t t = 0; t < tmp.size(); ++t) {
+      col[rowptr[i] + t] = tmp[t].first;
+      slot[rowptr[i] + t] = tmp[t].second;
+    }
+  }
+}
+
 extern "C" int hf_get_csr(hf_ctx* c, int32_t* rowptr, int32_t* col, double* val_A, double* val_M, double* val_A0) {
   if (!c || c->N == 0) return hf_fail(HF_ERR_STATE, "hf_get_csr: no mesh");
   cudaSetDevice(c->device);
-  if (rowptr) HF_TRY(c->rowptr.download(rowptr, c->N + 1, c->stream));
-  if (col) HF_TRY(c->col.download(col, c->nnz, c->stream));
-  if (val_A || val_M || val_A0) {
-    if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_get_csr: operator not built");
+  if ((val_A || val_M || val_A0) && !c->op_built) return hf_fail(HF_ERR_STATE, "hf_get_csr: operator not built");
+  if (!c->permuted) {
+    if (rowptr) std::copy(c->h_rowptr.begin(), c->h_rowptr.end(), rowptr);
+    if (col) std::copy(c->h_col.begin(), c->h_col.end(), col);
     if (val_A) HF_TRY(c->valA.download(val_A, c->nnz, c->stream));
     if (val_M) HF_TRY(c->valM.download(val_M, c->nnz, c->stream));
     if (val_A0) HF_TRY(c->valA0.download(val_A0, c->nnz, c->stream));
+    return HF_OK;
+  }
+  std::vector<int> rp, cl, slot;
+  user_pattern(c, rp, cl, slot);
+  if (rowptr) std::copy(rp.begin(), rp.end(), rowptr);
+  if (col) std::copy(cl.begin(), cl.end(), col);
+  std::vector<double> tmp(c->nnz);
+  const DevBuf<double>* src[3] = {&c->valA, &c->valM, &c->valA0};
+  double* dst[3] = {val_A, val_M, val_A0};
+  for (int a = 0; a < 3; ++a) {
+    if (!dst[a]) continue;
+    HF_TRY(src[a]->download(tmp.data(), c->nnz, c->stream));
+    for (int64_t k = 0; k < c->nnz; ++k) dst[a][k] = tmp[slot[k]];
   }
   return HF_OK;
 }
@@ -446,8 +675,7 @@ extern "C" int hf_get_csr(hf_ctx* c, int32_t* rowptr, int32_t* col, double* val_
 extern "C" int hf_set_state(hf_ctx* c, const double* u) {
   if (!c || !u || c->N == 0) return hf_fail(HF_ERR_ARG, "hf_set_state: bad arguments");
   cudaSetDevice(c->device);
-  HF_CUDA(cudaMemcpyAsync(c->u.p, u, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
-  HF_CUDA(cudaStreamSynchronize(c->stream));
+  HF_TRY(hf_upload_nodal(c, u, c->u.p));
   c->have_prev = false;
   return HF_OK;
 }
@@ -455,13 +683,13 @@ extern "C" int hf_set_state(hf_ctx* c, const double* u) {
 extern "C" int hf_get_state(hf_ctx* c, double* u) {
   if (!c || !u || c->N == 0) return hf_fail(HF_ERR_ARG, "hf_get_state: bad arguments");
   cudaSetDevice(c->device);
-  return c->u.download(u, c->N, c->stream);
+  return hf_download_nodal(c, c->u.p, u, 1);
 }
 
 extern "C" int hf_get_rhs(hf_ctx* c, double* b) {
   if (!c || !b || c->N == 0) return hf_fail(HF_ERR_ARG, "hf_get_rhs: bad arguments");
   cudaSetDevice(c->device);
-  return c->b.download(b, c->N, c->stream);
+  return hf_download_nodal(c, c->b.p, b, 1);
 }
 
 extern "C" int hf_set_source(hf_ctx* c, const double* s) {
@@ -478,8 +706,7 @@ extern "C" int hf_set_source(hf_ctx* c, const double* s) {
     k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 0.0, c->ck.p);
     HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valM1.p));
   }
-  HF_CUDA(cudaMemcpyAsync(c->source.p, s, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
-  HF_CUDA(cudaStreamSynchronize(c->stream));
+  HF_TRY(hf_upload_nodal(c, s, c->source.p));
   c->have_source = true;
   return HF_OK;
 }
@@ -648,10 +875,10 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
   if (!c || n_steps < 0 || (n_steps && !amp) || n_watch < 0 || (n_watch && (!watch_nodes || !hist)))
     return hf_fail(HF_ERR_ARG, "hf_run: bad arguments");
   cudaSetDevice(c->device);
-  for (int i = 0; i < n_watch; ++i)
-    if (watch_nodes[i] < 0 || watch_nodes[i] >= c->N) return hf_fail(HF_ERR_ARG, "hf_run: watch node out of range");
+  std::vector<int> wn;
+  if (hf_internal_nodes(c, n_watch, watch_nodes, wn) != HF_OK) return hf_fail(HF_ERR_ARG, "hf_run: watch node out of range");
   if (n_watch) {
-    HF_TRY(c->watch.upload(watch_nodes, n_watch, c->stream));
+    HF_TRY(c->watch.upload(wn.data(), n_watch, c->stream));
     if (c->hist.n < (size_t)n_steps * n_watch) HF_TRY(c->hist.alloc((size_t)n_steps * n_watch, c->stream));
   }
   bool persist = false;
@@ -670,8 +897,14 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
     if (n_watch) c->stat_launches += 1;
     if (n_watch)
       k_sample<<<(n_watch + 255) / 256, 256, 0, c->stream>>>(n_watch, c->watch.p, c->u.p, c->hist.p + (size_t)s * n_watch);
-    if (fields)
-      HF_CUDA(cudaMemcpyAsync(fields + (size_t)s * c->N, c->u.p, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    if (fields) {
+      const double* src = c->u.p;
+      if (c->permuted) {   // stream-ordered: the staging buffer is reused only after the copy below has run
+        k_gather_nodal<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, 1, c->rank_d.p, c->u.p, c->stage.p);
+        src = c->stage.p;
+      }
+      HF_CUDA(cudaMemcpyAsync(fields + (size_t)s * c->N, src, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    }
   }
   HF_CUDA(cudaEventRecord(c->ev1, c->stream));
   if (n_watch && n_steps)
@@ -709,11 +942,11 @@ extern "C" int hf_sample(hf_ctx* c, int32_t n, const int32_t* nodes, double* out
   if (!c || n < 0 || (n && (!nodes || !out))) return hf_fail(HF_ERR_ARG, "hf_sample: bad arguments");
   if (n == 0) return HF_OK;
   cudaSetDevice(c->device);
-  for (int i = 0; i < n; ++i)
-    if (nodes[i] < 0 || nodes[i] >= c->N) return hf_fail(HF_ERR_ARG, "hf_sample: node out of range");
+  std::vector<int> in;
+  if (hf_internal_nodes(c, n, nodes, in) != HF_OK) return hf_fail(HF_ERR_ARG, "hf_sample: node out of range");
   DevBuf<int> d;
   DevBuf<double> o;
-  HF_TRY(d.upload(nodes, n, c->stream));
+  HF_TRY(d.upload(in.data(), n, c->stream));
   HF_TRY(o.alloc(n, c->stream));
   k_sample<<<(n + 255) / 256, 256, 0, c->stream>>>(n, d.p, c->u.p, o.p);
   return o.download(out, n, c->stream);
@@ -738,6 +971,9 @@ __global__ void k_ctrl_force(HfCtrl* c, int nparts) {
     c->itA = 0;
     c->itB = 0;
     c->nparts = nparts;
+    c->alpha = 0.0;
+    c->beta = 0.0;
+    c->counter = 0u;
   }
 }
 int hf_spmv_device(hf_ctx* c, const SellOp& op);   // hf_pcg.cu
@@ -748,14 +984,15 @@ extern "C" int hf_spmv(hf_ctx* c, const double* x, double* y) {
   cudaSetDevice(c->device);
   PcgWork& w = c->ws;
   DevBuf<double> dx;
-  HF_TRY(dx.upload(x, c->N, c->stream));
+  HF_TRY(dx.alloc(c->N, c->stream));
+  HF_TRY(hf_upload_nodal(c, x, dx.p));
   const int g = (c->Npad + 255) / 256;
   k_scale_in<<<g, 256, 0, c->stream>>>(c->N, c->Npad, dx.p, c->opA.scale.p, w.r.p);
   k_ctrl_force<<<1, 256, 0, c->stream>>>(w.ctrl.p, w.grid);
   HF_TRY(hf_spmv_device(c, c->opA));
-  k_scale_out<<<g, 256, 0, c->stream>>>(c->N, w.q.p, c->opA.scale.p, dx.p);
+  k_scale_out<<<g, 256, 0, c->stream>>>(c->N, w.q1.p, c->opA.scale.p, dx.p);
   HF_CUDA(cudaGetLastError());
-  return dx.download(y, c->N, c->stream);
+  return hf_download_nodal(c, dx.p, y, 1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -845,5 +1082,5 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
   }
   c->last_iters = keep;
   if (iters_out) *iters_out = total;
-  return c->proj_g.download(grad, (size_t)2 * c->N, c->stream);
+  return hf_download_nodal(c, c->proj_g.p, grad, 2);
 }

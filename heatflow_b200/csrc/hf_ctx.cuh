@@ -75,6 +75,10 @@ struct HfCtrl {
   int itA;           // iteration counter read by the SpMV kernel (written by the update kernel)
   int itB;           // copy read by the update kernel (written by the SpMV kernel)
   int nparts;        // number of valid partial sums (= grid of the producing kernels)
+  double alpha;      // streaming kernel: step length of the iteration just finished
+  double beta;       //                   direction update factor of the next iteration
+  unsigned counter;  //                   CTAs that have published their partial sums
+  unsigned pad_;
   double part_rr[2][HF_MAX_PART];
   double part_pq[HF_MAX_PART];
   double part_bn[HF_MAX_PART];
@@ -88,6 +92,19 @@ struct SellView {
   const double* __restrict__ val;
 };
 
+// Patch view of the same operator for the streaming kernel: rows are cut into chunks of R
+// consecutive rows (one CTA each).  A chunk's columns are its own rows plus a short halo list, so
+// column indices are 16-bit positions in the CTA's shared-memory copy of the direction vector:
+// [0, R) = own rows, R + h = halo_idx[halo_ptr[chunk] + h].
+struct PatchView {
+  int nslices, R, nchunks;
+  const int* __restrict__ slice_ptr;
+  const unsigned short* __restrict__ lcol;
+  const double* __restrict__ val;
+  const int* __restrict__ halo_ptr;    // [nchunks+1]
+  const int* __restrict__ halo_idx;
+};
+
 struct SellOp {
   int nslices = 0;
   size_t padded_nnz = 0;
@@ -99,7 +116,13 @@ struct SellOp {
   int p_spw = 0, p_grid = 0, p_mat_cap = 0, p_sz_cap = 0;
   size_t p_smem = 0;
   DevBuf<int2> p_range;                // per CTA: [lo, hi) column range of its rows
+  // patch decomposition (streaming kernel)
+  int R = 0, nchunks = 0, halo_max = 0, mat_cap = 0;
+  DevBuf<unsigned short> lcol;
+  DevBuf<int> halo_ptr, halo_idx;
+  size_t iter_smem = 0;
   SellView view() const { return SellView{nslices, slice_ptr.p, col.p, val.p}; }
+  PatchView patch() const { return PatchView{nslices, R, nchunks, slice_ptr.p, lcol.p, val.p, halo_ptr.p, halo_idx.p}; }
   void drop_graphs() const {
     for (auto& g : chunk_exec) {
       if (g) cudaGraphExecDestroy(g);
@@ -111,6 +134,8 @@ struct SellOp {
 
 struct PcgWork {
   DevBuf<double> x, r, p0, p1, q;
+  DevBuf<double> r1, q1;               // second halves of the ping-pong pairs (streaming kernel)
+  DevBuf<double> parts;                // [4][max chunks] per-CTA partial sums (streaming kernel)
   DevBuf<HfCtrl> ctrl;
   DevBuf<uint4> slots;                 // flag-with-data reduction slots (persistent kernel)
   DevBuf<uint4> qpk;                   // [2][Npad] q = A p exchange packets (persistent kernel)
@@ -129,6 +154,13 @@ struct hf_ctx {
   cudaStream_t stream = nullptr;
   // mesh
   int N = 0, E = 0, nv = 3, Npad = 0;
+  // internal node numbering (locality order for the streaming kernels): internal = rank[user],
+  // user = order[internal].  Every C-ABI array is in the caller's numbering; the library permutes.
+  int ordering_req = 0;                // 0 auto, 1 as given, 2 Hilbert curve
+  bool permuted = false;
+  std::vector<int> h_rank, h_order;
+  DevBuf<int> rank_d, order_d;
+  DevBuf<double> stage;                // [2N] staging buffer of permuted host transfers
   DevBuf<double> xy;
   DevBuf<int> cells, cell_tag;
   DevBuf<int> n2c_ptr, n2c_idx;
@@ -207,6 +239,11 @@ __device__ __forceinline__ double hf_ld_stream(const double* p) {
   asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ int hf_ld_stream(const unsigned short* p) {
+  unsigned short v;
+  asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return (int)v;
+}
 __device__ __forceinline__ int hf_ld_stream(const int* p) {
   int v;
   asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -221,3 +258,8 @@ int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot);
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out);
 int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out);
 void hf_ens_free(hf_ctx* c);
+int hf_build_patches(const hf_ctx* c, int R, std::vector<int>& halo_ptr, std::vector<int>& halo_idx,
+                     std::vector<unsigned short>& lcol, int* halo_max);
+int hf_upload_nodal(hf_ctx* c, const double* h_user, double* d_internal);
+int hf_download_nodal(hf_ctx* c, const double* d_internal, double* h_user, int ncomp);
+int hf_internal_nodes(hf_ctx* c, int n, const int32_t* user_nodes, std::vector<int>& out);

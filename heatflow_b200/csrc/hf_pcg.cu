@@ -1,4 +1,4 @@
-// heatflow_b200 - Jacobi-preconditioned CG on the sliced-ELL scaled operator (sm_100a).
+// heatflow_b200 - Jacobi-preconditioned CG, streaming kernel: ONE launch per iteration (sm_100a).
 //
 // Replaces KSP PREONLY + PC LU / MUMPS (reference: run_with_diamond.py:389-394, :480).
 // Jacobi preconditioning is applied as the symmetric scaling  Ahat = D^-1/2 A D^-1/2,
@@ -6,112 +6,223 @@
 // Jacobi-PCG on A, needs no z = D^-1 r vector, and removes the SI-unit spread
 // (diagonals 1e-15 .. 1) from every norm and threshold.
 //
-// One iteration = two kernels, both bandwidth bound, no host involvement:
-//   k_pcg_spmv   : beta = rr/rr_old ; p = r + beta p (written to the other p buffer) ;
-//                  q = Ahat p, gathering r and p_old at the neighbour columns ; partial p.q
-//   k_pcg_update : alpha = rr/(p.q) ; x += alpha p ; r -= alpha q ; partial r.r
-// Every CTA re-reduces the per-CTA partial sums in a fixed order (warp shuffles + one smem
-// pass), so alpha, beta and the convergence test are bit-reproducible and device-side.
-// Algorithmic traffic per row and iteration (fp64 values, int32 columns, nnz ~ 7/row):
-//   spmv   12*nnz + 4/32 (slice ptr) + 8 (r) + 8 (p_old) + 8 (p_new) + 8 (q) ~ 116 B
-//   update 8*4 reads + 8*2 writes                                           =  48 B
+// Kernel n of a solve (k_pcg_iter) fuses the vector updates that finish iteration n-1 with the
+// SpMV and dot products of iteration n, on a patch decomposition of the rows (PatchView):
+//   phase 1  own rows + halo of the CTA's chunk, coalesced / short gather:
+//              x_n = x_{n-1} + alpha_{n-1} p_{n-1}        (own rows only)
+//              r_n = r_{n-1} - alpha_{n-1} q_{n-1}
+//              p_n = r_n + beta_n p_{n-1}                 -> shared memory (own + halo)
+//   phase 2  q_n = Ahat p_n from shared memory (16-bit local columns, sliced-ELL values streamed
+//            once, no global gathers) ; partial sums of r_n.r_n, p_n.q_n, r_n.q_n, q_n.q_n
+//   tail     the last CTA to finish adds the partials in CTA order (bit-reproducible):
+//              rr_n = r_n.r_n (direct)        -> convergence test, alpha_n = rr_n / p_n.q_n
+//              rr_{n+1} ~ rr_n - 2 alpha_n r_n.q_n + alpha_n^2 q_n.q_n   -> beta_{n+1}
+//            The identity for ||r_n - alpha q_n||^2 only feeds beta (rounding error ~eps*rr_n, and it
+//            never accumulates because the next kernel measures rr_{n+1} directly); alpha is always the
+//            exact line-search step of the direction actually used.
+// r, p and q are ping-pong pairs (a CTA reads its neighbours' old values while they write new ones).
+// Algorithmic traffic per row and iteration (fp64 values, 16-bit local columns, nnz ~ 7/row, halo
+// fraction h ~ 4/sqrt(R) with the Hilbert node order):
+//   matrix 10*nnz + 4/32 ; vectors: read x r p q (32 + 24 h), write x r p q (32)   ~ 136 + 24 h bytes
+// (textbook PCG with separate kernels: 232; the former two-kernel fusion: 164).
 #include <algorithm>
 #include <cmath>
-#include <cooperative_groups.h>
 
 #include "hf_ctx.cuh"
-
-namespace cg = cooperative_groups;
 
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HF_BLOCK)
-k_pcg_spmv(SellView A, const double* __restrict__ r, double* __restrict__ pbuf0,
-           double* __restrict__ pbuf1, double* __restrict__ q, HfCtrl* __restrict__ c) {
-  __shared__ double sh[HF_BLOCK / 32];
-  if (*(volatile int*)&c->done) return;
-  const int it = c->itA;
-  const int par = it & 1;
-  const int np = c->nparts;
-  const double rr = hf_sum_parts(c->part_rr[par], np, sh);
-  if (rr <= c->thr) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      c->rr = rr;
-      c->done = 1;
-    }
-    return;
-  }
-  double beta = 0.0;
-  if (it > 0) beta = rr / hf_sum_parts(c->part_rr[par ^ 1], np, sh);
-  const double* __restrict__ po = par ? pbuf1 : pbuf0;
-  double* __restrict__ pn = par ? pbuf0 : pbuf1;
-  if (blockIdx.x == 0 && threadIdx.x == 0) c->itB = it;
+__device__ __forceinline__ unsigned hf_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-  const int lane = threadIdx.x & 31;
-  const int wpb = HF_BLOCK / 32;
-  double local = 0.0;
-  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < A.nslices; s += gridDim.x * wpb) {
-    const int base = A.slice_ptr[s];
-    const int w = (A.slice_ptr[s + 1] - base) >> 5;
-    const int row = s * HF_SLICE + lane;
-    const int* cp = A.col + base + lane;
-    const double* vp = A.val + base + lane;
-    double acc = 0.0;
-    if (it > 0) {
-#pragma unroll 4
-      for (int k = 0; k < w; ++k) {
-        const int cj = hf_ld_stream(cp + k * 32);
-        const double v = hf_ld_stream(vp + k * 32);
-        acc = fma(v, fma(beta, __ldg(po + cj), __ldg(r + cj)), acc);
-      }
-    } else {
-#pragma unroll 4
-      for (int k = 0; k < w; ++k) {
-        const int cj = hf_ld_stream(cp + k * 32);
-        const double v = hf_ld_stream(vp + k * 32);
-        acc = fma(v, __ldg(r + cj), acc);
-      }
-    }
-    const double pi = (it > 0) ? fma(beta, __ldg(po + row), __ldg(r + row)) : __ldg(r + row);
-    pn[row] = pi;
-    q[row] = acc;
-    local = fma(pi, acc, local);
-  }
-  const double tot = hf_block_sum(local, sh);
-  if (threadIdx.x == 0) c->part_pq[blockIdx.x] = tot;
+// TMA bulk copy global -> shared (cp.async.bulk, SASS UBLKCP), completion counted on an mbarrier.
+// Addresses and size must be multiples of 16 bytes.
+__device__ __forceinline__ void hf_bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   hf_smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(hf_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void hf_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hf_smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void hf_mbar_expect(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hf_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hf_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "HF_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra HF_DONE;\n"
+      "bra HF_WAIT;\n"
+      "HF_DONE:\n"
+      "}\n" ::"r"(hf_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
+#define HF_BULK_PIECE 16384u   // bytes per cp.async.bulk
+
+template <int RPT>   // rows per thread in phase 1: chunk size R = HF_BLOCK * RPT
 __global__ void __launch_bounds__(HF_BLOCK)
-k_pcg_update(int n2 /* Npad/2 */, double2* __restrict__ x, double2* __restrict__ r,
-             const double2* __restrict__ pbuf0, const double2* __restrict__ pbuf1,
-             const double2* __restrict__ q, HfCtrl* __restrict__ c) {
-  __shared__ double sh[HF_BLOCK / 32];
-  if (*(volatile int*)&c->done) return;
-  const int it = c->itB;
-  const int par = it & 1;
-  const int np = c->nparts;
-  const double rr = hf_sum_parts(c->part_rr[par], np, sh);
-  const double pq = hf_sum_parts(c->part_pq, np, sh);
-  const double alpha = rr / pq;
-  const double2* __restrict__ p = par ? pbuf0 : pbuf1;   // the buffer k_pcg_spmv just wrote
-  double local = 0.0;
-  for (int i = blockIdx.x * HF_BLOCK + threadIdx.x; i < n2; i += gridDim.x * HF_BLOCK) {
-    const double2 pv = p[i], qv = q[i];
-    double2 xv = x[i], rv = r[i];
-    xv.x = fma(alpha, pv.x, xv.x);
-    xv.y = fma(alpha, pv.y, xv.y);
-    rv.x = fma(-alpha, qv.x, rv.x);
-    rv.y = fma(-alpha, qv.y, rv.y);
-    x[i] = xv;
-    r[i] = rv;
-    local = fma(rv.x, rv.x, local);
-    local = fma(rv.y, rv.y, local);
+k_pcg_iter(PatchView A, int par, int mat_cap, double* __restrict__ x, double* __restrict__ rb0, double* __restrict__ rb1,
+           double* __restrict__ pb0, double* __restrict__ pb1, double* __restrict__ qb0, double* __restrict__ qb1,
+           double* __restrict__ parts, HfCtrl* __restrict__ c) {
+  constexpr int R = HF_BLOCK * RPT;
+  constexpr int SPC = R / HF_SLICE;     // slices per chunk
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double* sval = reinterpret_cast<double*>(smraw);                            // [mat_cap] operator values of the chunk
+  unsigned short* scol = reinterpret_cast<unsigned short*>(sval + mat_cap);   // [mat_cap] local columns
+  double* sp = reinterpret_cast<double*>(scol + mat_cap);                     // p_n: own rows [0,R), halo [R, R+nh)
+  __shared__ double sh4[4][HF_BLOCK / 32];
+  __shared__ double tot[4];
+  __shared__ int s_last;
+  __shared__ int s_ctl_i[2];
+  __shared__ double s_ctl_d[2];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lo = blockIdx.x * R;
+  const int s_first = blockIdx.x * SPC, s_end = min(s_first + SPC, A.nslices);
+  const int hp0 = A.halo_ptr[blockIdx.x], nh = A.halo_ptr[blockIdx.x + 1] - hp0;
+  double* sr = sp + R + nh;             // r_n on own rows
+  const double* __restrict__ ro = par ? rb1 : rb0;
+  const double* __restrict__ po = par ? pb1 : pb0;
+  const double* __restrict__ qo = par ? qb1 : qb0;
+  double* __restrict__ rn = par ? rb0 : rb1;
+  double* __restrict__ pn = par ? pb0 : pb1;
+  double* __restrict__ qn = par ? qb0 : qb1;
+  // ---- thread 0: control block (ONE reader per CTA: every CTA of the grid polls the same L2 line) and the
+  // operator block of the chunk -> shared memory by TMA bulk copies (in flight during phase 1)
+  const int e0 = A.slice_ptr[s_first];
+  if (tid == 0) {
+    const int d = *(volatile int*)&c->done;
+    s_ctl_i[0] = d;
+    s_ctl_i[1] = *(volatile int*)&c->itA;
+    s_ctl_d[0] = *(volatile double*)&c->alpha;
+    s_ctl_d[1] = *(volatile double*)&c->beta;
+    if (d == 0) {
+      const unsigned n = (unsigned)(A.slice_ptr[s_end] - e0);
+      hf_mbar_init(&mbar, 1);
+      hf_mbar_expect(&mbar, n * 10u);
+      for (unsigned off = 0; off < n * 8u; off += HF_BULK_PIECE)
+        hf_bulk_g2s(reinterpret_cast<unsigned char*>(sval) + off, reinterpret_cast<const unsigned char*>(A.val + e0) + off,
+                    min(HF_BULK_PIECE, n * 8u - off), &mbar);
+      for (unsigned off = 0; off < n * 2u; off += HF_BULK_PIECE)
+        hf_bulk_g2s(reinterpret_cast<unsigned char*>(scol) + off, reinterpret_cast<const unsigned char*>(A.lcol + e0) + off,
+                    min(HF_BULK_PIECE, n * 2u - off), &mbar);
+    }
   }
-  const double tot = hf_block_sum(local, sh);
-  if (threadIdx.x == 0) {
-    c->part_rr[par ^ 1][blockIdx.x] = tot;
-    if (blockIdx.x == 0) c->itA = it + 1;
+  // ---- phase 1: all vector loads are issued before the control block is needed
+  double xv[RPT], rv[RPT], pv[RPT], qv[RPT];
+#pragma unroll
+  for (int t = 0; t < RPT; ++t) {
+    const int g = lo + t * HF_BLOCK + tid;
+    xv[t] = x[g];
+    rv[t] = ro[g];
+    pv[t] = po[g];
+    qv[t] = qo[g];
+  }
+  __syncthreads();                      // control block (and the mbarrier init) visible to the CTA
+  const int done = s_ctl_i[0], it = s_ctl_i[1];
+  const double alpha = s_ctl_d[0], beta = s_ctl_d[1];
+  if (done) return;                     // uniform over the grid: thread 0 has not started a copy either
+  double l_rr = 0.0;
+#pragma unroll
+  for (int t = 0; t < RPT; ++t) {
+    const int i = t * HF_BLOCK + tid;
+    double r_new = rv[t], p_new = rv[t];
+    if (it > 0) {
+      x[lo + i] = fma(alpha, pv[t], xv[t]);
+      r_new = fma(-alpha, qv[t], rv[t]);
+      p_new = fma(beta, pv[t], r_new);
+    }
+    rn[lo + i] = r_new;
+    pn[lo + i] = p_new;
+    sp[i] = p_new;
+    sr[i] = r_new;
+    l_rr = fma(r_new, r_new, l_rr);
+  }
+  for (int h = tid; h < nh; h += HF_BLOCK) {
+    const int g = A.halo_idx[hp0 + h];
+    const double r_old = ro[g];
+    double p_new = r_old;
+    if (it > 0) p_new = fma(beta, po[g], fma(-alpha, qo[g], r_old));
+    sp[R + h] = p_new;
+  }
+  __syncthreads();                      // sp/sr complete
+  hf_mbar_wait(&mbar, 0);               // operator block has landed
+  // ---- phase 2: q = Ahat p, everything from shared memory
+  double l_pq = 0.0, l_rq = 0.0, l_qq = 0.0;
+  for (int sl = warp; s_first + sl < s_end; sl += HF_BLOCK / 32) {
+    const int base = A.slice_ptr[s_first + sl] - e0;
+    const int w = (A.slice_ptr[s_first + sl + 1] - e0 - base) >> 5;
+    const unsigned short* cp = scol + base + lane;
+    const double* vp = sval + base + lane;
+    double acc0 = 0.0, acc1 = 0.0;
+    int k = 0;
+    for (; k + 2 <= w; k += 2) {
+      acc0 = fma(vp[k * 32], sp[cp[k * 32]], acc0);
+      acc1 = fma(vp[(k + 1) * 32], sp[cp[(k + 1) * 32]], acc1);
+    }
+    if (k < w) acc0 = fma(vp[k * 32], sp[cp[k * 32]], acc0);
+    const double acc = acc0 + acc1;
+    const int i = sl * HF_SLICE + lane;
+    qn[lo + i] = acc;
+    l_pq = fma(sp[i], acc, l_pq);
+    l_rq = fma(sr[i], acc, l_rq);
+    l_qq = fma(acc, acc, l_qq);
+  }
+  // ---- per-CTA partials (one barrier for the four sums), last CTA finalises the iteration
+  const int G = gridDim.x;
+  {
+    const double v0 = hf_warp_sum(l_rr), v1 = hf_warp_sum(l_pq), v2 = hf_warp_sum(l_rq), v3 = hf_warp_sum(l_qq);
+    if (lane == 0) {
+      sh4[0][warp] = v0;
+      sh4[1][warp] = v1;
+      sh4[2][warp] = v2;
+      sh4[3][warp] = v3;
+    }
+  }
+  __syncthreads();
+  if (tid < 4) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < HF_BLOCK / 32; ++i) t += sh4[tid][i];
+    __stcg(parts + tid * G + blockIdx.x, t);
+    __threadfence();
+  }
+  __syncwarp();
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(&c->counter, 1u);
+    s_last = (ticket == (unsigned)G - 1u);
+    if (s_last) c->counter = 0u;
+    __threadfence();
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // warp a sums quantity a over the CTAs in a fixed order
+  if (warp < 4) {
+    double v = 0.0;
+    for (int i = lane; i < G; i += 32) v += __ldcg(parts + warp * G + i);
+    v = hf_warp_sum(v);
+    if (lane == 0) tot[warp] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double rr = tot[0];
+    c->rr = rr;
+    if (!(rr > c->thr)) {               // also stops on NaN
+      c->done = 1;
+    } else {
+      const double al = rr / tot[1];
+      const double rr_next = fma(al * al, tot[3], fma(-2.0 * al, tot[2], rr));
+      c->alpha = al;
+      c->beta = fmax(rr_next, 0.0) / rr;
+      c->itA = it + 1;
+    }
   }
 }
 
@@ -141,6 +252,9 @@ __global__ void __launch_bounds__(HF_BLOCK) k_pcg_ctrl_init(HfCtrl* c, int npart
     c->itA = 0;
     c->itB = 0;
     c->nparts = nparts;
+    c->alpha = 0.0;
+    c->beta = 0.0;
+    c->counter = 0u;
   }
 }
 
@@ -149,12 +263,15 @@ __global__ void __launch_bounds__(HF_BLOCK) k_pcg_ctrl_init(HfCtrl* c, int npart
 // ---------------------------------------------------------------------------------------
 int hf_pcg_alloc(hf_ctx* c) {
   PcgWork& w = c->ws;
-  const size_t n = (size_t)c->Npad;
+  // padded to the largest chunk size of the streaming kernel (rows >= Npad stay zero)
+  const size_t n = ((size_t)c->Npad + 1023) / 1024 * 1024;
   HF_TRY(w.x.alloc(n, c->stream));
   HF_TRY(w.r.alloc(n, c->stream));
   HF_TRY(w.p0.alloc(n, c->stream));
   HF_TRY(w.p1.alloc(n, c->stream));
   HF_TRY(w.q.alloc(n, c->stream));
+  HF_TRY(w.r1.alloc(n, c->stream));
+  HF_TRY(w.q1.alloc(n, c->stream));
   HF_TRY(w.ctrl.alloc(1, c->stream));
   if (!w.h_ctrl) HF_CUDA(cudaMallocHost(&w.h_ctrl, sizeof(double) * 3 + sizeof(int) * 4));
   const int nslices = c->Npad / HF_SLICE;
@@ -165,21 +282,42 @@ int hf_pcg_alloc(hf_ctx* c) {
 
 static const int kChunk[3] = {8, 32, 128};
 
-static int launch_iteration(hf_ctx* c, const SellOp& op) {
+static int launch_iteration(hf_ctx* c, const SellOp& op, int par) {
   PcgWork& w = c->ws;
-  k_pcg_spmv<<<w.grid, HF_BLOCK, 0, c->stream>>>(op.view(), w.r.p, w.p0.p, w.p1.p, w.q.p, w.ctrl.p);
-  k_pcg_update<<<w.grid, HF_BLOCK, 0, c->stream>>>(c->Npad / 2, (double2*)w.x.p, (double2*)w.r.p,
-                                                   (const double2*)w.p0.p, (const double2*)w.p1.p,
-                                                   (const double2*)w.q.p, w.ctrl.p);
+  const PatchView A = op.patch();
+  const size_t sm = op.iter_smem;
+  switch (op.R) {
+    case 1024:
+      k_pcg_iter<4><<<op.nchunks, HF_BLOCK, sm, c->stream>>>(A, par, op.mat_cap, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
+      break;
+    case 512:
+      k_pcg_iter<2><<<op.nchunks, HF_BLOCK, sm, c->stream>>>(A, par, op.mat_cap, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
+      break;
+    default:
+      k_pcg_iter<1><<<op.nchunks, HF_BLOCK, sm, c->stream>>>(A, par, op.mat_cap, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
+      break;
+  }
+  return HF_OK;
+}
+
+static int set_iter_smem(const SellOp& op) {
+  // per function, not per operator: raise the limit right before use
+  const int sm = (int)op.iter_smem;
+  if (sm > 48 * 1024) {
+    if (op.R == 1024) HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else if (op.R == 512) HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    else HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  }
   return HF_OK;
 }
 
 static int build_chunks(hf_ctx* c, const SellOp& op) {
   op.drop_graphs();
+  HF_TRY(set_iter_smem(op));
   for (int k = 0; k < 3; ++k) {
     cudaGraph_t g;
     HF_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < kChunk[k]; ++i) launch_iteration(c, op);
+    for (int i = 0; i < kChunk[k]; ++i) launch_iteration(c, op, i & 1);   // chunk lengths are even: parity = iteration parity
     HF_CUDA(cudaStreamEndCapture(c->stream, &g));
     HF_CUDA(cudaGraphInstantiate(&op.chunk_exec[k], g, 0));
     HF_CUDA(cudaGraphDestroy(g));
@@ -193,6 +331,7 @@ static int build_chunks(hf_ctx* c, const SellOp& op) {
 int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out) {
   PcgWork& w = c->ws;
   if (!op.chunk_exec[0]) HF_TRY(build_chunks(c, op));
+  if (op.iter_smem > 48 * 1024) HF_TRY(set_iter_smem(op));
   const size_t hdr = sizeof(double) * 3 + sizeof(int) * 4;
   int launched = 0;
   // first burst: what the previous solve needed (time steps are similar), then short chunks
@@ -204,7 +343,7 @@ int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out
       HF_CUDA(cudaGraphLaunch(op.chunk_exec[k], c->stream));
       want -= kChunk[k];
       launched += kChunk[k];
-      c->stat_launches += 2ull * kChunk[k];
+      c->stat_launches += (unsigned long long)kChunk[k];
     }
     HF_CUDA(cudaMemcpyAsync(w.h_ctrl, w.ctrl.p, hdr, cudaMemcpyDeviceToHost, c->stream));
     HF_CUDA(cudaStreamSynchronize(c->stream));
@@ -219,6 +358,7 @@ int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out
     }
     want = std::max(32, launched / 4);
   }
+  if (!std::isfinite(w.h_ctrl->rr)) return hf_fail(HF_ERR_NOCONV, "PCG: non-finite residual");
   const int its = w.h_ctrl->itA;
   c->last_iters = its;
   c->stat_iters += its;
@@ -247,11 +387,11 @@ int hf_pcg_prepare(hf_ctx* c) {
   return HF_OK;
 }
 
-// q = Ahat r through the production SpMV kernel (first-iteration path, beta = 0); the caller has
-// forced the control block with k_ctrl_force.
+// q1 = Ahat r through the production kernel (iteration-0 path: p = r); the caller has forced the
+// control block with k_ctrl_force.  The result is in ws.q1.
 int hf_spmv_device(hf_ctx* c, const SellOp& op) {
-  PcgWork& w = c->ws;
-  k_pcg_spmv<<<w.grid, HF_BLOCK, 0, c->stream>>>(op.view(), w.r.p, w.p0.p, w.p1.p, w.q.p, w.ctrl.p);
+  HF_TRY(set_iter_smem(op));
+  HF_TRY(launch_iteration(c, op, 0));
   HF_CUDA(cudaGetLastError());
   return HF_OK;
 }
@@ -264,19 +404,15 @@ __global__ void k_flush(unsigned char* p, size_t n) {
     ((uint4*)p)[i] = make_uint4(i, 0, 0, 0);
 }
 
-__global__ void k_bench_ctrl(HfCtrl* c, int nparts) {
-  // keep alpha = beta = 1e-30-ish harmless values: rr = nparts, pq = nparts * 1e30
-  for (int i = threadIdx.x; i < HF_MAX_PART; i += blockDim.x) {
-    c->part_rr[0][i] = 1.0;
-    c->part_rr[1][i] = 1.0;
-    c->part_pq[i] = 1e30;
-  }
+__global__ void k_bench_ctrl(HfCtrl* c) {
+  // steady-state iteration with harmless scalars (alpha ~ 1e-30: the vectors change by rounding only)
   if (threadIdx.x == 0) {
     c->thr = 0.0;
     c->done = 0;
     c->itA = 2;
-    c->itB = 2;
-    c->nparts = nparts;
+    c->alpha = 1e-30;
+    c->beta = 0.5;
+    c->counter = 0u;
   }
 }
 
@@ -288,32 +424,27 @@ extern "C" int hf_bench_kernels(hf_ctx* c, int32_t reps, int32_t flush_l2, float
   cudaEvent_t e0, e1;
   HF_CUDA(cudaEventCreate(&e0));
   HF_CUDA(cudaEventCreate(&e1));
-  // save x, r (the benchmark perturbs them by ~1e-30 relative; restore afterwards)
+  HF_TRY(set_iter_smem(c->opA));
+  // the benchmark perturbs x, r, p by ~1e-30 relative: save and restore x and r
   DevBuf<double> sx, sr;
   HF_TRY(sx.alloc(c->Npad, c->stream));
   HF_TRY(sr.alloc(c->Npad, c->stream));
   HF_CUDA(cudaMemcpyAsync(sx.p, w.x.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
   HF_CUDA(cudaMemcpyAsync(sr.p, w.r.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
-  double acc[2] = {0.0, 0.0};
-  for (int which = 0; which < 2; ++which) {
-    for (int rep = -3; rep < reps; ++rep) {
-      k_bench_ctrl<<<1, 256, 0, c->stream>>>(w.ctrl.p, w.grid);
-      if (flush_l2) k_flush<<<c->sm_count * 4, 256, 0, c->stream>>>(c->flush.p, fl);
-      HF_CUDA(cudaEventRecord(e0, c->stream));
-      if (which == 0)
-        k_pcg_spmv<<<w.grid, HF_BLOCK, 0, c->stream>>>(c->opA.view(), w.r.p, w.p0.p, w.p1.p, w.q.p, w.ctrl.p);
-      else
-        k_pcg_update<<<w.grid, HF_BLOCK, 0, c->stream>>>(c->Npad / 2, (double2*)w.x.p, (double2*)w.r.p,
-                                                         (const double2*)w.p0.p, (const double2*)w.p1.p,
-                                                         (const double2*)w.q.p, w.ctrl.p);
-      HF_CUDA(cudaEventRecord(e1, c->stream));
-      HF_CUDA(cudaEventSynchronize(e1));
-      float ms = 0.f;
-      HF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-      if (rep >= 0) acc[which] += ms;
-    }
-    ms_out[which] = (float)(acc[which] / reps);
+  double acc = 0.0;
+  for (int rep = -3; rep < reps; ++rep) {
+    k_bench_ctrl<<<1, 32, 0, c->stream>>>(w.ctrl.p);
+    if (flush_l2) k_flush<<<c->sm_count * 4, 256, 0, c->stream>>>(c->flush.p, fl);
+    HF_CUDA(cudaEventRecord(e0, c->stream));
+    HF_TRY(launch_iteration(c, c->opA, rep & 1));
+    HF_CUDA(cudaEventRecord(e1, c->stream));
+    HF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep >= 0) acc += ms;
   }
+  ms_out[0] = (float)(acc / reps);
+  ms_out[1] = 0.f;                      // the update is fused into the iteration kernel
   HF_CUDA(cudaMemcpyAsync(w.x.p, sx.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
   HF_CUDA(cudaMemcpyAsync(w.r.p, sr.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));

@@ -403,6 +403,8 @@ int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot) {
   a.sz_cap = op.p_sz_cap;
   void* args[] = {&a};
   const void* fn = (const void*)k_pcg_persist<4>;
+  // the attribute is per function, not per operator: other operators / contexts may have lowered it
+  HF_CUDA(cudaFuncSetAttribute(k_pcg_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.p_smem));
   HF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(op.p_grid), dim3(HF_PT), args, op.p_smem, c->stream));
   c->stat_launches += 1;
   return HF_OK;

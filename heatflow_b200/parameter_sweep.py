@@ -1,0 +1,413 @@
+#!/usr/bin/env python3
+"""Parameter sweep over laser FWHM, sample conductivity and sample width on the GPU.
+
+Drop-in for the reference ``parameter_sweep.py`` (same functions, arguments, CLI flags, run-folder
+naming and summary files: parameter_sweep.py:56-121 watchers, :123-192 single run, :195-268 grid /
+cfg editing, :290-540 driver, :543-604 CLI).  What differs is how the runs execute:
+
+  reference                                      here
+  ---------------------------------------------  ---------------------------------------------
+  one spawned CPU process per parameter set,     variants of a width group (same mesh) advance in
+  each re-reading the mesh, re-assembling and    tiles of ``batch`` simulations through the batched
+  LU-factorising (``mp.Pool``)                   multi-RHS CUDA kernels; tiles are sharded over the
+                                                 GPUs (torchrun ranks, or ``num_processes`` spawned
+                                                 GPU workers) with one final gather of the watcher
+                                                 histories (``mode='ensemble'``, the default)
+  ---------------------------------------------  ---------------------------------------------
+  ``mode='per_run'`` (forced by ``write_xdmf=True``) keeps the reference's behaviour of calling
+  ``run_simulation`` once per parameter set, which also writes the XDMF and gradient CSV files.
+
+The runner follows the cfg: ``run_with_diamond`` when the cfg has diamond anvils (``p_diam``),
+``run_no_diamond`` otherwise (the reference imports ``run_no_diamond`` only, but its own
+``get_watcher_points`` already handles both stacks, parameter_sweep.py:85-103).
+"""
+import argparse
+import copy
+import itertools
+import json
+import multiprocessing as mp
+import os
+import time
+from datetime import datetime
+
+import numpy as np
+import pandas as pd
+import yaml
+
+from . import problem, sweep
+from .runners import Simulation2D, suppress_output
+
+
+def set_single_thread():
+    """Set environment variables to ensure single-threaded host libraries (parameter_sweep.py:46-53)."""
+    for var in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'VECLIB_MAXIMUM_THREADS',
+                'NUMEXPR_NUM_THREADS', 'BLIS_NUM_THREADS'):
+        os.environ[var] = '1'
+
+
+def initialize_worker():
+    """Worker initialiser (parameter_sweep.py:56-66; there is no MPI to initialise here)."""
+    set_single_thread()
+
+
+def get_watcher_points(cfg):
+    """Watcher points halfway through the iridium coupler layers, ``{'pside': (z, r), 'oside': (z, r)}``
+    (parameter_sweep.py:69-120)."""
+    z_sample = float(cfg['mats']['p_sample']['z'])
+    z_ins_pside = float(cfg['mats']['p_ins']['z'])
+    z_ins_oside = float(cfg['mats']['o_ins']['z'])
+    z_coupler = float(cfg['mats']['p_coupler']['z'])
+    if 'p_diam' in cfg['mats']:
+        z_diam = float(cfg['mats']['p_diam']['z'])
+        mesh_zmin = -(z_sample / 2) - z_ins_pside - z_coupler - z_diam
+        mesh_zmax = (z_sample / 2) + z_ins_oside + z_coupler + z_diam
+        bnd_p_ins_end = mesh_zmin + z_diam + z_ins_pside
+        bnd_o_ins_start = mesh_zmax - z_diam - z_ins_oside
+    else:
+        mesh_zmin = -(z_sample / 2) - z_ins_pside - z_coupler
+        mesh_zmax = (z_sample / 2) + z_ins_oside + z_coupler
+        bnd_p_ins_end = mesh_zmin + z_ins_pside
+        bnd_o_ins_start = mesh_zmax - z_ins_oside
+    return {'pside': (bnd_p_ins_end + z_coupler / 2, 0.0), 'oside': (bnd_o_ins_start - z_coupler / 2, 0.0)}
+
+
+def _runner_for(cfg):
+    if 'p_diam' in cfg['mats']:
+        from .run_with_diamond import run_simulation
+        return run_simulation, problem.stack_with_diamond
+    from .run_no_diamond import run_simulation
+    return run_simulation, problem.stack_no_diamond
+
+
+def run_name_for(fwhm, k, width):
+    """Run folder name (parameter_sweep.py:145)."""
+    return f"fwhm_{fwhm:.2e}_k_{k:.2f}_width_{width:.2e}".replace('+', '').replace('-0', '-')
+
+
+def run_single_simulation(args):
+    """One parameter set through ``run_simulation`` (parameter_sweep.py:123-192).
+
+    args = (combo, base_config, mesh_folder, output_dir, write_xdmf, suppress_print, run_id)
+    """
+    set_single_thread()
+    combo, base_config, mesh_folder, output_dir, write_xdmf, suppress_print, run_id = args
+    fwhm, k, width = combo['fwhm'], combo['k'], combo['width']
+    run_name = run_name_for(fwhm, k, width)
+    run_output_dir = os.path.join(output_dir, run_name)
+    config = modify_config_for_parameters(base_config, fwhm, k, width)
+    watcher_points = get_watcher_points(config)
+    result = {'run_id': run_id, 'run_name': run_name, 'fwhm': fwhm, 'k': k, 'width': width,
+              'output_dir': run_output_dir}
+    try:
+        start_time = time.time()
+        run_simulation, _ = _runner_for(config)
+        run_simulation(cfg=config, mesh_folder=mesh_folder, rebuild_mesh=False, visualize_mesh=False,
+                       output_folder=run_output_dir, watcher_points=watcher_points, write_xdmf=write_xdmf,
+                       suppress_print=suppress_print)
+        result.update(runtime=time.time() - start_time, status='success', error=None)
+    except Exception as e:
+        result.update(runtime=0.0, status='failed', error=str(e))
+    return result
+
+
+def create_parameter_grid(fwhm_range, k_range, width_range, num_points):
+    """Log-spaced FWHM and k, linearly spaced width, grouped by width (parameter_sweep.py:195-237)."""
+    fwhm_min, fwhm_max = fwhm_range
+    k_min, k_max = k_range
+    width_min, width_max = width_range
+    num_fwhm, num_k, num_width = num_points
+    fwhm_vals = np.logspace(np.log10(fwhm_min), np.log10(fwhm_max), num_fwhm)
+    k_vals = np.logspace(np.log10(k_min), np.log10(k_max), num_k)
+    width_vals = np.linspace(width_min, width_max, num_width)
+    parameter_combinations = []
+    for width in width_vals:
+        for fwhm, k in itertools.product(fwhm_vals, k_vals):
+            parameter_combinations.append({'fwhm': fwhm, 'k': k, 'width': width})
+    return parameter_combinations, fwhm_vals, k_vals, width_vals
+
+
+def modify_config_for_parameters(base_config, fwhm, k, width):
+    """Copy of ``base_config`` with heating.fwhm, mats.p_sample.k and mats.p_sample.z replaced
+    (parameter_sweep.py:240-268)."""
+    config = copy.deepcopy(base_config)
+    config['heating']['fwhm'] = float(fwhm)
+    config['mats']['p_sample']['k'] = float(k)
+    config['mats']['p_sample']['z'] = float(width)
+    return config
+
+
+def get_mesh_folder_for_width(base_mesh_folder, width):
+    """``<base>/width_<w>`` (parameter_sweep.py:271-288)."""
+    width_str = f"{width:.3e}".replace('+', '').replace('-0', '-')
+    return os.path.join(base_mesh_folder, f"width_{width_str}")
+
+
+# ----------------------------------------------------------------------------------------
+# ensemble execution of one width group
+# ----------------------------------------------------------------------------------------
+def _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print):
+    """Set the group's mesh up on ``device`` and run this rank's tiles.
+    Returns (idx, hist, iters, secs, errors, step_times)."""
+    cfg0 = modify_config_for_parameters(base_config, combinations[0]['fwhm'], combinations[0]['k'], combinations[0]['width'])
+    _, stack = _runner_for(cfg0)
+    with suppress_output(suppress_print):
+        sim = Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device)
+    try:
+        watch = sim.watcher_nodes(list(get_watcher_points(cfg0).values()))
+        fwhm = np.array([c['fwhm'] for c in combinations])
+        k = np.array([c['k'] for c in combinations])
+        out = sweep.run_tiles(sim, fwhm, k, tiles, watch)
+        return out + (sim.step_t.copy(),)
+    finally:
+        sim.close()
+
+
+def _device_worker(args):
+    """Spawned GPU worker (one per device) for sweeps launched without torchrun."""
+    set_single_thread()
+    base_config, combinations, mesh_folder, batch, device, tiles, suppress_print = args
+    return _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print)
+
+
+def _write_run_outputs(output_dir, base_config, combo, step_t, hist, names):
+    run_dir = os.path.join(output_dir, run_name_for(combo['fwhm'], combo['k'], combo['width']))
+    os.makedirs(run_dir, exist_ok=True)
+    config = modify_config_for_parameters(base_config, combo['fwhm'], combo['k'], combo['width'])
+    with open(os.path.join(run_dir, 'used_config.yaml'), 'w') as f:
+        yaml.safe_dump(config, f)
+    df = pd.DataFrame({'time': step_t})
+    for w, name in enumerate(names):
+        df[name] = hist[:, w]
+    df.to_csv(os.path.join(run_dir, 'watcher_points.csv'), index=False)
+    return run_dir
+
+
+def _visible_gpus():
+    from . import _lib
+    return int(_lib.load().hf_device_count())
+
+
+def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width_range, num_points,
+                        base_mesh_folder="meshes", write_xdmf=False, suppress_print=True, num_processes=None,
+                        mode="ensemble", batch=16):
+    """Run the sweep (parameter_sweep.py:290-540).  Returns ``(results, failed_runs)`` on rank 0
+    (``([], [])`` on the other torchrun ranks).
+
+    ``num_processes``: GPU worker processes when not launched under torchrun (default: every
+    visible GPU).  ``mode``: 'ensemble' (batched kernels, ``batch`` variants per tile) or 'per_run'.
+    """
+    set_single_thread()
+    if mode not in ("ensemble", "per_run"):
+        raise ValueError("mode must be 'ensemble' or 'per_run'")
+    if write_xdmf:
+        mode = "per_run"                       # field output needs every state on the host
+    if not 1 <= int(batch) <= 32:
+        raise ValueError("batch must be in [1, 32]")
+    rank, world, local_rank = sweep.dist_info()
+
+    with open(base_config_path, 'r') as f:
+        base_config = yaml.safe_load(f)
+    parameter_combinations, fwhm_vals, k_vals, width_vals = create_parameter_grid(fwhm_range, k_range, width_range, num_points)
+
+    n_gpus = _visible_gpus()
+    if n_gpus < 1:
+        raise RuntimeError("parameter_sweep: no CUDA device (heatflow_b200 has no CPU fallback)")
+    n_workers = 1 if world > 1 else max(1, min(n_gpus, num_processes or n_gpus))
+
+    if rank == 0:
+        os.makedirs(output_dir, exist_ok=True)
+        sweep_metadata = {
+            'base_config': base_config_path, 'fwhm_range': fwhm_range, 'k_range': k_range, 'width_range': width_range,
+            'num_points': num_points, 'fwhm_values': fwhm_vals.tolist(), 'k_values': k_vals.tolist(),
+            'width_values': width_vals.tolist(), 'total_runs': len(parameter_combinations),
+            'num_processes': world if world > 1 else n_workers, 'timestamp': datetime.now().isoformat(),
+            'execution': {'mode': mode, 'batch': int(batch), 'gpus': world if world > 1 else n_workers},
+            'watcher_points': {
+                'description': 'Temperature monitoring points positioned halfway through iridium coupler layers',
+                'locations': {'pside': 'Center of p-side iridium coupler (r=0)', 'oside': 'Center of o-side iridium coupler (r=0)'},
+                'coordinates': 'Relative to mesh geometry, calculated for each parameter combination'}}
+        with open(os.path.join(output_dir, 'sweep_metadata.json'), 'w') as f:
+            json.dump(sweep_metadata, f, indent=2)
+
+    width_groups = {}
+    for combo in parameter_combinations:
+        width_groups.setdefault(combo['width'], []).append(combo)
+
+    results, failed_runs = [], []
+    total_completed = 0
+    say = print if rank == 0 else (lambda *a, **k: None)
+    say(f"Starting parameter sweep with {len(parameter_combinations)} total runs")
+    say(f"Parameters: {len(fwhm_vals)} FWHM values, {len(k_vals)} k values, {len(width_vals)} width values")
+    say(f"Grouped into {len(width_groups)} width groups for mesh reuse")
+    say(f"Using {world if world > 1 else n_workers} GPU(s), mode={mode}, batch={batch}")
+    say(f"Output directory: {output_dir}")
+    say("Watcher points: Temperature monitoring at iridium coupler centers (pside, oside)")
+    say("-" * 80)
+
+    for width_idx, (width, combinations) in enumerate(width_groups.items()):
+        say(f"\nProcessing width group {width_idx + 1}/{len(width_groups)}: width = {width:.2e} m")
+        say(f"  {len(combinations)} runs for this width")
+        mesh_folder = get_mesh_folder_for_width(base_mesh_folder, width)
+        mesh_file = os.path.join(mesh_folder, 'mesh.msh')
+        mesh_cfg_file = os.path.join(mesh_folder, 'mesh_cfg.yaml')
+        if rank == 0:
+            os.makedirs(mesh_folder, exist_ok=True)
+            if not (os.path.exists(mesh_file) and os.path.exists(mesh_cfg_file)):
+                say(f"  Building new mesh for width {width:.2e} m")
+                config = modify_config_for_parameters(base_config, combinations[0]['fwhm'], combinations[0]['k'], width)
+                _, stack = _runner_for(config)
+                from .runners import prepare_mesh
+                with suppress_output(suppress_print):
+                    prepare_mesh(config, stack, mesh_folder, rebuild_mesh=True)
+            else:
+                say(f"  Reusing existing mesh for width {width:.2e} m")
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+        names = list(get_watcher_points(base_config).keys())
+        if mode == "per_run":
+            # the reference's own scheme: one run_simulation per parameter set (this rank's share)
+            mine = list(range(len(combinations)))[rank::world]
+            local = [run_single_simulation((combinations[i], base_config, mesh_folder, output_dir, write_xdmf, suppress_print,
+                                            total_completed + i + 1)) for i in mine]
+            if world > 1:
+                import torch.distributed as dist
+                bucket = [None] * world if rank == 0 else None
+                dist.gather_object(local, bucket, dst=0)
+                local = [r for part in bucket for r in part] if rank == 0 else []
+            for result in sorted(local, key=lambda r: r['run_id']):
+                total_completed += 1
+                (results if result['status'] == 'success' else failed_runs).append(result)
+                _report(say, result, total_completed, len(parameter_combinations))
+            if rank != 0:
+                total_completed += len(combinations)
+            continue
+
+        tiles = sweep.plan_tiles([c['k'] for c in combinations], int(batch), world if world > 1 else n_workers)
+        say(f"  Starting {len(combinations)} simulations in {sum(len(t) for t in tiles)} tile(s) of <= {batch}...")
+        S = int(base_config['timing']['num_steps'])
+        t_group = time.time()
+        if world > 1 or n_workers == 1:
+            idx, hist, iters, secs, errors, step_t = _group_on_device(base_config, combinations, mesh_folder, batch,
+                                                                      local_rank if world > 1 else 0, tiles[rank], suppress_print)
+            gathered = sweep.gather_results(len(combinations), S, len(names), idx, hist, iters, secs, errors)
+        else:
+            if mp.get_start_method(allow_none=True) != 'spawn':
+                try:
+                    mp.set_start_method('spawn', force=True)
+                except RuntimeError:
+                    pass
+            jobs = [(base_config, combinations, mesh_folder, batch, d, tiles[d], suppress_print) for d in range(n_workers)]
+            with mp.Pool(processes=n_workers, initializer=initialize_worker) as pool:
+                parts = pool.map(_device_worker, jobs)
+            hist = np.full((len(combinations), S, len(names)), np.nan)
+            iters = np.full(len(combinations), -1, dtype=np.int64)
+            secs = np.zeros(len(combinations))
+            errors = {}
+            for idx_p, hist_p, it_p, sec_p, err_p, step_t in parts:
+                hist[idx_p], iters[idx_p], secs[idx_p] = hist_p, it_p, sec_p
+                errors.update(err_p)
+            gathered = (hist, iters, secs, errors)
+        if rank != 0:
+            total_completed += len(combinations)
+            continue
+        hist, iters, secs, errors = gathered
+        say(f"  group finished in {time.time() - t_group:.2f}s")
+        for i, combo in enumerate(combinations):
+            total_completed += 1
+            run_name = run_name_for(combo['fwhm'], combo['k'], combo['width'])
+            result = {'run_id': total_completed, 'run_name': run_name, 'fwhm': combo['fwhm'], 'k': combo['k'],
+                      'width': combo['width'], 'output_dir': os.path.join(output_dir, run_name)}
+            if i in errors or not np.all(np.isfinite(hist[i])):
+                result.update(runtime=0.0, status='failed', error=errors.get(i, 'non-finite watcher history'))
+                failed_runs.append(result)
+            else:
+                _write_run_outputs(output_dir, base_config, combo, step_t, hist[i], names)
+                result.update(runtime=float(secs[i]), status='success', error=None)
+                results.append(result)
+            _report(say, result, total_completed, len(parameter_combinations))
+
+    if rank != 0:
+        return [], []
+    results_df = pd.DataFrame(results)
+    if not results_df.empty:
+        results_df.to_csv(os.path.join(output_dir, 'successful_runs.csv'), index=False)
+    failed_df = pd.DataFrame(failed_runs)
+    if not failed_df.empty:
+        failed_df.to_csv(os.path.join(output_dir, 'failed_runs.csv'), index=False)
+
+    print("\n" + "=" * 80)
+    print("PARAMETER SWEEP COMPLETE")
+    print("=" * 80)
+    print(f"Total runs: {len(parameter_combinations)}")
+    print(f"Successful: {len(results)}")
+    print(f"Failed: {len(failed_runs)}")
+    print(f"Results saved to: {output_dir}")
+    if results:
+        avg_runtime = np.mean([r['runtime'] for r in results])
+        total_runtime = sum(r['runtime'] for r in results)
+        print(f"Average runtime per simulation: {avg_runtime:.2f}s")
+        print(f"Total simulation time: {total_runtime:.2f}s")
+    return results, failed_runs
+
+
+def _report(say, result, done, total):
+    head = f"[{done}/{total}] FWHM={result['fwhm']:.2e}m, k={result['k']:.2f}W/m/K, width={result['width']:.2e}m"
+    if result['status'] == 'success':
+        say(f"  ✓ {head} - Completed in {result['runtime']:.2f}s")
+    else:
+        say(f"  ✗ {head} - Failed: {result['error']}")
+
+
+def main():
+    """Command-line interface (parameter_sweep.py:543-604) plus --mode / --batch."""
+    parser = argparse.ArgumentParser(description='Parameter sweep for heatflow simulations')
+    parser.add_argument('--config', type=str, required=True, help='Path to base configuration file')
+    parser.add_argument('--output-dir', type=str, required=True, help='Directory to save all results')
+    parser.add_argument('--fwhm-range', type=float, nargs=2, default=[1e-6, 1e-4], help='FWHM range in meters (min max)')
+    parser.add_argument('--k-range', type=float, nargs=2, default=[1.0, 100.0],
+                        help='Thermal conductivity range in W/m/K (min max)')
+    parser.add_argument('--width-range', type=float, nargs=2, default=[1e-6, 10e-6],
+                        help='Sample width range in meters (min max)')
+    parser.add_argument('--num-points', type=int, nargs=3, default=[5, 5, 3],
+                        help='Number of points for each parameter (fwhm k width)')
+    parser.add_argument('--mesh-folder', type=str, default='meshes', help='Base directory for mesh storage')
+    parser.add_argument('--write-xdmf', action='store_true', help='Write XDMF output files (forces --mode per_run)')
+    parser.add_argument('--verbose', action='store_true', help='Show detailed output during simulations')
+    parser.add_argument('--num-processes', type=int, default=None, help='Number of GPU workers (default: all visible GPUs)')
+    parser.add_argument('--mode', choices=['ensemble', 'per_run'], default='ensemble')
+    parser.add_argument('--batch', type=int, default=16, help='Variants per ensemble tile (1..32)')
+    args = parser.parse_args()
+
+    if any(x <= 0 for x in args.num_points):
+        parser.error("Number of points must be positive")
+    if args.fwhm_range[0] <= 0 or args.fwhm_range[1] <= 0:
+        parser.error("FWHM range must be positive")
+    if args.k_range[0] <= 0 or args.k_range[1] <= 0:
+        parser.error("Thermal conductivity range must be positive")
+    if args.width_range[0] <= 0 or args.width_range[1] <= 0:
+        parser.error("Width range must be positive")
+    if args.num_processes is not None and args.num_processes <= 0:
+        parser.error("Number of processes must be positive")
+
+    # under torchrun every rank runs this script; join the process group for the final gather
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    try:
+        run_parameter_sweep(base_config_path=args.config, output_dir=args.output_dir, fwhm_range=tuple(args.fwhm_range),
+                            k_range=tuple(args.k_range), width_range=tuple(args.width_range),
+                            num_points=tuple(args.num_points), base_mesh_folder=args.mesh_folder,
+                            write_xdmf=args.write_xdmf, suppress_print=not args.verbose, num_processes=args.num_processes,
+                            mode=args.mode, batch=args.batch)
+    finally:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

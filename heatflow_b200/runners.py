@@ -108,20 +108,24 @@ def configure_solver(domain, cell_tags, materials, mat_tag_map, bcs, gaussian_bc
     return solver
 
 
-def run_2d(cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, output_folder=None,
-           watcher_points=None, write_xdmf=True, suppress_print=False, radial_outputs=False,
-           progress_splits=5, device=0):
-    with suppress_output(suppress_print):
-        program_start_time = time.time()
-        materials, info, domain, cell_tags, mat_tag_map = prepare_mesh(cfg, stack, mesh_folder, rebuild_mesh)
+class Simulation2D:
+    """cfg + mesh folder -> configured ``HeatSolver`` plus everything the time loop needs
+    (set-up half of the reference runners, run_with_diamond.py:183-394)."""
+
+    def __init__(self, cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, device=0,
+                 rtol=DEFAULT_RTOL, max_iters=DEFAULT_MAX_ITERS):
+        self.cfg = cfg
+        self.materials, self.info, self.domain, self.cell_tags, self.mat_tag_map = prepare_mesh(
+            cfg, stack, mesh_folder, rebuild_mesh)
         if visualize_mesh:
             print("visualize_mesh: the gmsh GUI is not available in this build - skipped")
-        r_sample = info["r_sample"]
+        materials, domain, cell_tags, mat_tag_map = self.materials, self.domain, self.cell_tags, self.mat_tag_map
+        r_sample = self.info["r_sample"]
         p_coupler = next(m for m in materials if m.name == "p_coupler")
 
-        heat_t, heat_T = problem.read_heating_curve(cfg['heating']['file'])
+        self.heat_t, self.heat_T = heat_t, heat_T = problem.read_heating_curve(cfg['heating']['file'])
 
-        V = fem.functionspace(domain, ("Lagrange", 1))
+        self.V = V = fem.functionspace(domain, ("Lagrange", 1))
         print('Assigning material properties...')
         unknown = set(np.unique(cell_tags.values)) - {mat_tag_map[m.name] for m in materials}
         if unknown:
@@ -129,11 +133,10 @@ def run_2d(cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, ou
         print('Material properties assigned.')
 
         t_final = float(cfg['timing']['t_final'])
-        num_steps = int(cfg['timing']['num_steps'])
-        dt = t_final / num_steps
-        ic_temp = float(cfg['heating']['ic_temp'])
-        heating_FWHM = float(cfg['heating']['fwhm'])
-        coeff = problem.gaussian_coeff(heating_FWHM)
+        self.num_steps = num_steps = int(cfg['timing']['num_steps'])
+        self.dt = dt = t_final / num_steps
+        self.ic_temp = ic_temp = float(cfg['heating']['ic_temp'])
+        self.coeff = coeff = problem.gaussian_coeff(float(cfg['heating']['fwhm']))
         offset = heat_T[0] - ic_temp
 
         def heating_offset(t):
@@ -142,12 +145,38 @@ def run_2d(cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, ou
         def gaussian(x, y, t):
             return (heating_offset(t) - ic_temp) * np.exp(coeff * (y - 0.0) ** 2) + ic_temp
 
-        obj_bcs = problem.standard_bcs(V, p_coupler.boundaries[0], r_sample, ic_temp, gaussian)
-        inner_bc = obj_bcs[3]
+        self.obj_bcs = problem.standard_bcs(V, p_coupler.boundaries[0], r_sample, ic_temp, gaussian)
+        self.inner_bc = self.obj_bcs[3]
+        self.solver = configure_solver(domain, cell_tags, materials, mat_tag_map, self.obj_bcs, self.inner_bc, dt,
+                                       device=device, rtol=rtol, max_iters=max_iters, ic_temp=ic_temp)
+        self.n_dofs = domain.geometry.x.shape[0]
+        self.mesh_coords = domain.geometry.x[:, :2]
+        self.step_t = (np.arange(num_steps) + 1) * dt
+        self.amps = problem.heating_amplitudes(self.step_t, heat_t, heat_T, ic_temp)
 
-        solver = configure_solver(domain, cell_tags, materials, mat_tag_map, obj_bcs, inner_bc, dt,
-                                  device=device, ic_temp=ic_temp)
-        n_dofs = domain.geometry.x.shape[0]
+    def watcher_nodes(self, watcher_coords):
+        """Nearest mesh node of every watcher point (run_with_diamond.py:443-449)."""
+        if not len(watcher_coords):
+            return []
+        tree = cKDTree(self.mesh_coords)
+        return [int(tree.query(coords)[1]) for coords in watcher_coords]
+
+    def sample_tag(self, name="p_sample"):
+        return int(self.mat_tag_map[name])
+
+    def close(self):
+        self.solver.close()
+
+
+def run_2d(cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, output_folder=None,
+           watcher_points=None, write_xdmf=True, suppress_print=False, radial_outputs=False,
+           progress_splits=5, device=0):
+    with suppress_output(suppress_print):
+        program_start_time = time.time()
+        sim = Simulation2D(cfg, stack, mesh_folder, rebuild_mesh, visualize_mesh, device)
+        domain, solver = sim.domain, sim.solver
+        num_steps, dt, ic_temp, coeff = sim.num_steps, sim.dt, sim.ic_temp, sim.coeff
+        n_dofs = sim.n_dofs
 
         if output_folder is not None:
             save_folder = output_folder
@@ -168,12 +197,9 @@ def run_2d(cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, ou
             xdmf.write_mesh(domain)
             xdmf.write_function(u_n, 0.0)
 
-        mesh_coords = domain.geometry.x[:, :2]
+        mesh_coords = sim.mesh_coords
         watcher_names, watcher_coords = _watchers(watcher_points)
-        watcher_nodes = []
-        if watcher_points is not None:
-            tree = cKDTree(mesh_coords)
-            watcher_nodes = [int(tree.query(coords)[1]) for coords in watcher_coords]
+        watcher_nodes = sim.watcher_nodes(watcher_coords) if watcher_points is not None else []
         watcher_data = {name: [] for name in watcher_names}
         watcher_time = []
 
@@ -186,8 +212,7 @@ def run_2d(cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, ou
         loop_start_time = time.time()
         print('Beginning loop...')
         startup_time = time.time() - program_start_time
-        step_t = (np.arange(num_steps) + 1) * dt
-        amps = problem.heating_amplitudes(step_t, heat_t, heat_T, ic_temp)
+        step_t, amps = sim.step_t, sim.amps
         per_step_host_work = write_xdmf or radial_outputs
         step = 0
         while step < num_steps:

@@ -32,6 +32,7 @@ class HeatSolver:
         self.n = 0
         self.n_bc = 0
         self.bc_dofs = np.zeros(0, np.int32)
+        self.ens_batch = 0
 
     # -- lifetime -------------------------------------------------------------------
     def close(self):
@@ -52,6 +53,11 @@ class HeatSolver:
         self.close()
 
     # -- problem set-up -------------------------------------------------------------
+    def set_ordering(self, ordering):
+        """Internal node order of the device data: 'auto', 'given' or 'hilbert' (before set_mesh)."""
+        code = {"auto": 0, "given": 1, "hilbert": 2}.get(ordering, ordering)
+        _lib.check(self._L.hf_set_ordering(self._h, int(code)))
+
     def set_mesh(self, nodes, cells, cell_tag):
         """nodes [N,2] (z, r) or [N] / [N,1] for interval meshes; cells [E,3] or [E,2]."""
         nodes = _f64(nodes)
@@ -209,3 +215,4 @@ class HeatSolver:
 
     def ens_destroy(self):
         _lib.check(self._L.hf_ens_destroy(self._h))
+        self.ens_batch = 0

@@ -38,6 +38,12 @@ int hf_device_count(void);
 hf_ctx* hf_create(int device);
 void hf_destroy(hf_ctx* ctx);
 
+/* Internal node numbering used for the device data structures: 0 = auto (default), 1 = as given,
+ * 2 = Hilbert-curve order (compact 2-D patches per CTA; what the streaming and ensemble kernels
+ * want).  Call before hf_set_mesh.  Purely internal: every array crossing this ABI stays in the
+ * caller's numbering, which is also the dof numbering (dolfinx P1: dof i = node i). */
+int hf_set_ordering(hf_ctx* ctx, int32_t ordering);
+
 /* Mesh arrays as gmshio.model_to_mesh would hand them to dolfinx
  * (reference: run_with_diamond.py:240-245): node coordinates xy[N,2] = (z, r), cell
  * connectivity cells[E,nv] (nv = 3 triangles, nv = 2 intervals for the 1-D path,

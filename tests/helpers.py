@@ -77,9 +77,10 @@ def make_oracle(c):
     return ho.Oracle2D(c.nodes, c.tris, c.rhoc_c, c.kappa_c, c.dt, c.oracle_bcs, c.ic, c.fwhm, c.heat_t, c.heat_T)
 
 
-def make_solver(c, rtol=1e-14, warm=0.0, mode=0):
+def make_solver(c, rtol=1e-14, warm=0.0, mode=0, ordering="auto"):
     from heatflow_b200.solver import HeatSolver
     s = HeatSolver(0)
+    s.set_ordering(ordering)
     s.set_mesh(c.nodes, c.tris, c.cell_tag)
     s.set_materials(c.tags, c.kappa_t, c.rhoc_t)
     s.set_bcs(c.bc_dofs, c.bc_value, c.gauss_slot, c.gauss_r)

@@ -106,6 +106,39 @@ def test_history_every_step(name, mode):
     s.close()
 
 
+def test_hilbert_internal_ordering_is_invisible(small_wd):
+    """Every array crossing the C-ABI stays in the caller's numbering when the library renumbers
+    the nodes internally (Hilbert order): pattern, values, SpMV, RHS, histories, fields, gradient."""
+    c = small_wd
+    s = make_solver(c, ordering="hilbert")
+    g = make_solver(c, ordering="given")
+    O = make_oracle(c)
+    rowptr, col, A, M, A0 = s.csr()
+    rowptr_g, col_g, A_g, M_g, A0_g = g.csr()
+    assert np.array_equal(rowptr, O.rowptr) and np.array_equal(col, O.col)
+    assert np.array_equal(A, A_g) and np.array_equal(M, M_g) and np.array_equal(A0, A0_g)   # same bits, same slots
+    x = np.random.default_rng(3).standard_normal(len(c.nodes))
+    y, want = s.spmv(x), O.A @ x
+    assert np.all(np.abs(y - want) <= 1e-14 * (np.abs(O.A) @ np.abs(x)))
+    watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.9e-6, 0.0)])
+    hist, iters, fields = s.run(c.amps[:30], c.ic, c.coeff, watch, keep_fields=True)
+    ohist, ofields = O.run(30, watch, keep_fields=True)
+    assert max(np.abs(f / of - 1).max() for f, of in zip(fields, ofields)) <= RTOL_FIELD
+    assert np.abs(hist / ohist - 1).max() <= RTOL_FIELD
+    assert np.array_equal(hist, np.array([f[watch] for f in fields]))
+    assert np.array_equal(s.get_state(), fields[-1]) and np.array_equal(s.sample(watch), hist[-1])
+    assert np.all(np.abs(s.get_rhs() - O.b) <= 1e-13 * np.abs(O.b).max())
+    P = ho.GradientProjector(c.nodes, c.tris)
+    want = P.project(s.get_state())
+    got = s.project_gradient()
+    assert np.all(np.abs(got - want).max(axis=0) <= 1e-9 * np.abs(want).max(axis=0))
+    u = c.ic + np.arange(len(c.nodes), dtype=float)
+    s.set_state(u)
+    assert np.array_equal(s.get_state(), u)
+    s.close()
+    g.close()
+
+
 def test_constant_state_invariance(small_wd):
     # all BCs = ic and u0 = ic: the state must stay ic to rounding (SURVEY section 4)
     c = small_wd

@@ -19,14 +19,15 @@ def probe(name, scale, warm=0.0, mode=0, steps=None):
           f"iters total={tot} max={iters.max()} time={dt:.3f}s -> {n*len(amps)/dt/1e6:.2f} MDOF-steps/s, "
           f"{dt/max(tot,1)*1e6:.2f} us/iter | kernels flushed spmv={ms_f[0]*1e3:.1f}us upd={ms_f[1]*1e3:.1f}us "
           f"warm spmv={ms_w[0]*1e3:.1f}us upd={ms_w[1]*1e3:.1f}us", flush=True)
-    bytes_spmv = 12 * nnz + 4 * n / 32 + 32 * n
-    print(f"   spmv algorithmic GB/s: flushed {bytes_spmv/ms_f[0]/1e6:.0f}  warm {bytes_spmv/ms_w[0]/1e6:.0f};"
-          f" update GB/s: flushed {48*n/ms_f[1]/1e6:.0f} warm {48*n/ms_w[1]/1e6:.0f}", flush=True)
+    bytes_iter = 10 * nnz + 4 * n / 32 + 64 * n
+    print(f"   k_pcg_iter algorithmic GB/s: flushed {bytes_iter/ms_f[0]/1e6:.0f}  warm {bytes_iter/ms_w[0]/1e6:.0f}", flush=True)
     s.close()
 
 if __name__ == "__main__":
-    for mode in (1, 2):
-        probe("geballe_no_diamond", 1.0, mode=mode)
-        probe("geballe_with_diamond", 1.0, mode=mode)
-    probe("geballe_with_diamond", 1.0, warm=1.0, mode=2)
-    probe("geballe_with_diamond", 0.7, mode=0, steps=30)
+    args = sys.argv[1:]
+    if args:
+        probe(args[0], float(args[1]), mode=int(args[2]), steps=int(args[3]) if len(args) > 3 else None)
+    else:
+        for mode in (1, 2):
+            probe("geballe_with_diamond", 1.0, mode=mode)
+        probe("geballe_with_diamond", 0.35, mode=0, steps=10)
