@@ -520,11 +520,12 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   op.drop_graphs();
   op.nslices = nsl;
   op.padded_nnz = (size_t)sp[nsl];
-  // chunk size of the streaming kernel: one CTA per chunk, at least ~3 CTAs per SM when the mesh allows
-  op.R = (c->Npad >= 3 * c->sm_count * 1024) ? 1024 : (c->Npad >= 3 * c->sm_count * 512) ? 512 : 256;
+  // chunk size of the streaming kernel (one persistent CTA per SM walks the chunks): 512 rows when every
+  // CTA still gets >= 8 chunks, else 256
+  op.R = (c->Npad >= 8 * c->sm_count * 512) ? 512 : 256;
   if (const char* env = getenv("HF_CHUNK_R")) {   // tuning knob
     const int r = atoi(env);
-    if (r == 256 || r == 512 || r == 1024) op.R = r;
+    if (r == 256 || r == 512) op.R = r;
   }
   op.nchunks = (c->Npad + op.R - 1) / op.R;
   op.mat_cap = 0;
@@ -535,21 +536,28 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   std::vector<int> hptr, hidx;
   std::vector<unsigned short> lcol;
   HF_TRY(hf_build_patches(c, op.R, hptr, hidx, lcol, &op.halo_max));
-  // operator block (values + 16-bit columns) + p (own + halo) + r (own)
-  op.iter_smem = (size_t)op.mat_cap * 10 + sizeof(double) * ((size_t)2 * op.R + op.halo_max);
+  // shared-memory stage: operator block (values + 16-bit columns) + x r q p (own rows) + halo p
+  op.halo_cap = (op.halo_max + 1) & ~1;
+  op.stage_bytes = (((size_t)op.mat_cap * 10 + sizeof(double) * ((size_t)4 * op.R + op.halo_cap) + 4 * (op.R / HF_SLICE + 4)) + 127) &
+                   ~(size_t)127;
   {
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
-    if (op.iter_smem + 1024 > (size_t)max_smem)
+    op.nstages = (int)std::min<size_t>(4, ((size_t)max_smem - 2048) / op.stage_bytes);
+    if (const char* env = getenv("HF_STAGES")) op.nstages = std::max(1, std::min(op.nstages, atoi(env)));
+    if (op.nstages < 1)
       return hf_fail(HF_ERR_STATE, "streaming PCG chunk does not fit in shared memory (halo of " + std::to_string(op.halo_max) +
                                        " rows); use hf_set_ordering(ctx, 2)");
+    op.iter_smem = op.stage_bytes * op.nstages;
   }
   DevBuf<unsigned short> lcol_csr;
   HF_TRY(lcol_csr.upload(lcol.data(), lcol.size(), c->stream));
   HF_TRY(op.halo_ptr.upload(hptr.data(), hptr.size(), c->stream));
   if (hidx.empty()) hidx.push_back(0);
   HF_TRY(op.halo_idx.upload(hidx.data(), hidx.size(), c->stream));
-  HF_TRY(op.slice_ptr.upload(sp.data(), nsl + 1, c->stream));
+  const int sp_end = sp[nsl];
+  sp.resize((size_t)op.nchunks * (op.R / HF_SLICE) + 5, sp_end);   // whole chunks + 4: zero-width padding slices
+  HF_TRY(op.slice_ptr.upload(sp.data(), sp.size(), c->stream));
   HF_TRY(op.col.alloc(op.padded_nnz, c->stream));
   HF_TRY(op.lcol.alloc(op.padded_nnz, c->stream));
   HF_TRY(op.val.alloc(op.padded_nnz, c->stream));
@@ -568,7 +576,7 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   HF_TRY(bad.download(&hbad, 1, c->stream));   // also orders the kernels before lcol_csr is freed
   if (hbad) return hf_fail(HF_ERR_STATE, "operator has a non-positive diagonal at row " + std::to_string(hbad - 1) +
                                              " (unset material or degenerate cell?)");
-  if (c->ws.parts.n < (size_t)4 * op.nchunks) HF_TRY(c->ws.parts.alloc((size_t)4 * op.nchunks, c->stream));
+  if (c->ws.parts.n < (size_t)4 * c->sm_count) HF_TRY(c->ws.parts.alloc((size_t)4 * c->sm_count, c->stream));
   return HF_OK;
 }
 

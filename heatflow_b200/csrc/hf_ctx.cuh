@@ -117,7 +117,8 @@ struct SellOp {
   size_t p_smem = 0;
   DevBuf<int2> p_range;                // per CTA: [lo, hi) column range of its rows
   // patch decomposition (streaming kernel)
-  int R = 0, nchunks = 0, halo_max = 0, mat_cap = 0;
+  int R = 0, nchunks = 0, halo_max = 0, mat_cap = 0, halo_cap = 0, nstages = 0;
+  size_t stage_bytes = 0;
   DevBuf<unsigned short> lcol;
   DevBuf<int> halo_ptr, halo_idx;
   size_t iter_smem = 0;

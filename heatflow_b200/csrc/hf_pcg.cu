@@ -43,6 +43,26 @@ __device__ __forceinline__ void hf_bulk_g2s(void* dst_smem, const void* src, uns
                "l"(src), "r"(bytes), "r"(hf_smem_u32(bar))
                : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy): the operator is streamed once per iteration
+// (evict_first) so that the PCG vectors, re-read every iteration, keep their L2 lines
+__device__ __forceinline__ void hf_bulk_g2s_hint(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar,
+                                                 unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          hf_smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(hf_smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long hf_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long hf_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void hf_mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hf_smem_u32(bar)), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -66,37 +86,69 @@ __device__ __forceinline__ void hf_mbar_wait(unsigned long long* bar, unsigned p
 
 #define HF_BULK_PIECE 16384u   // bytes per cp.async.bulk
 
-template <int RPT>   // rows per thread in phase 1: chunk size R = HF_BLOCK * RPT
-__global__ void __launch_bounds__(HF_BLOCK)
-k_pcg_iter(PatchView A, int par, int mat_cap, double* __restrict__ x, double* __restrict__ rb0, double* __restrict__ rb1,
+// Shared-memory stage of one chunk (byte offsets; every block is a multiple of 16 bytes):
+//   val[mat_cap] f64 | x[R] | r[R] | q[R] | p[R] | halo p[halo_cap] | lcol[mat_cap] u16 | slice_ptr[R/32 + 4] i32
+// After phase 1 the r block holds r_n and the p block + halo block hold p_n (own rows, then halo).
+struct IterStage {
+  int mat_cap, halo_cap, nstages;
+  unsigned stage_bytes;
+};
+
+template <int R>
+__device__ __forceinline__ void hf_issue_chunk(const PatchView& A, int ch, int e0, int e1, unsigned char* st, int mat_cap,
+                                               int halo_cap, const double* x, const double* ro, const double* po,
+                                               const double* qo, unsigned long long* bar) {
+  constexpr int SPC = R / HF_SLICE;
+  const unsigned n = (unsigned)(e1 - e0);
+  const unsigned vb = (unsigned)R * 8u;
+  unsigned char* sx = st + (size_t)mat_cap * 8;
+  unsigned char* scol = sx + 4 * (size_t)vb + (size_t)halo_cap * 8;
+  unsigned char* sptr = scol + (size_t)mat_cap * 2;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was last touched by ordinary loads/stores
+  hf_mbar_expect(bar, n * 10u + 4u * vb + (SPC + 4) * 4u);
+  const size_t lo = (size_t)ch * R;
+  const unsigned long long keep = hf_policy_evict_last(), stream = hf_policy_evict_first();
+  hf_bulk_g2s_hint(sx, x + lo, vb, bar, keep);
+  hf_bulk_g2s_hint(sx + vb, ro + lo, vb, bar, keep);
+  hf_bulk_g2s_hint(sx + 2 * vb, qo + lo, vb, bar, keep);
+  hf_bulk_g2s_hint(sx + 3 * vb, po + lo, vb, bar, keep);
+  hf_bulk_g2s(sptr, A.slice_ptr + (size_t)ch * SPC, (SPC + 4) * 4u, bar);   // slice_ptr is padded to whole chunks + 4
+  for (unsigned off = 0; off < n * 8u; off += HF_BULK_PIECE)
+    hf_bulk_g2s_hint(st + off, reinterpret_cast<const unsigned char*>(A.val + e0) + off, min(HF_BULK_PIECE, n * 8u - off), bar, stream);
+  for (unsigned off = 0; off < n * 2u; off += HF_BULK_PIECE)
+    hf_bulk_g2s_hint(scol + off, reinterpret_cast<const unsigned char*>(A.lcol + e0) + off, min(HF_BULK_PIECE, n * 2u - off), bar,
+                     stream);
+}
+
+#define HF_IT 512              // threads per CTA of the iteration kernel
+
+// Persistent: one CTA per SM walks the chunks blockIdx.x, blockIdx.x + gridDim.x, ...; the operator
+// block and the own-row vectors of the next chunks stream into the other shared-memory stages by TMA
+// while the current chunk is processed.  Halo values travel through a three-deep register pipeline
+// (chunk j: values, chunk j+1: node indices, chunk j+2: list extents), so no global-load latency is
+// exposed inside the chunk loop.
+template <int R>
+__global__ void __launch_bounds__(HF_IT, 1)
+k_pcg_iter(PatchView A, int par, IterStage S, double* __restrict__ x, double* __restrict__ rb0, double* __restrict__ rb1,
            double* __restrict__ pb0, double* __restrict__ pb1, double* __restrict__ qb0, double* __restrict__ qb1,
            double* __restrict__ parts, HfCtrl* __restrict__ c) {
-  constexpr int R = HF_BLOCK * RPT;
   constexpr int SPC = R / HF_SLICE;     // slices per chunk
+  constexpr int NW = HF_IT / 32;
   extern __shared__ __align__(128) unsigned char smraw[];
-  double* sval = reinterpret_cast<double*>(smraw);                            // [mat_cap] operator values of the chunk
-  unsigned short* scol = reinterpret_cast<unsigned short*>(sval + mat_cap);   // [mat_cap] local columns
-  double* sp = reinterpret_cast<double*>(scol + mat_cap);                     // p_n: own rows [0,R), halo [R, R+nh)
-  __shared__ double sh4[4][HF_BLOCK / 32];
-  __shared__ double tot[4];
-  __shared__ int s_last;
+  __shared__ double sh4[4][NW];
   __shared__ int s_ctl_i[2];
   __shared__ double s_ctl_d[2];
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long full[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lo = blockIdx.x * R;
-  const int s_first = blockIdx.x * SPC, s_end = min(s_first + SPC, A.nslices);
-  const int hp0 = A.halo_ptr[blockIdx.x], nh = A.halo_ptr[blockIdx.x + 1] - hp0;
-  double* sr = sp + R + nh;             // r_n on own rows
+  const int G = gridDim.x;
   const double* __restrict__ ro = par ? rb1 : rb0;
   const double* __restrict__ po = par ? pb1 : pb0;
   const double* __restrict__ qo = par ? qb1 : qb0;
   double* __restrict__ rn = par ? rb0 : rb1;
   double* __restrict__ pn = par ? pb0 : pb1;
   double* __restrict__ qn = par ? qb0 : qb1;
-  // ---- thread 0: control block (ONE reader per CTA: every CTA of the grid polls the same L2 line) and the
-  // operator block of the chunk -> shared memory by TMA bulk copies (in flight during phase 1)
-  const int e0 = A.slice_ptr[s_first];
+  const int nloc = (A.nchunks - (int)blockIdx.x + G - 1) / G;     // chunks of this CTA
+  // ---- thread 0: control block (ONE reader per CTA) and the first stages
   if (tid == 0) {
     const int d = *(volatile int*)&c->done;
     s_ctl_i[0] = d;
@@ -104,79 +156,132 @@ k_pcg_iter(PatchView A, int par, int mat_cap, double* __restrict__ x, double* __
     s_ctl_d[0] = *(volatile double*)&c->alpha;
     s_ctl_d[1] = *(volatile double*)&c->beta;
     if (d == 0) {
-      const unsigned n = (unsigned)(A.slice_ptr[s_end] - e0);
-      hf_mbar_init(&mbar, 1);
-      hf_mbar_expect(&mbar, n * 10u);
-      for (unsigned off = 0; off < n * 8u; off += HF_BULK_PIECE)
-        hf_bulk_g2s(reinterpret_cast<unsigned char*>(sval) + off, reinterpret_cast<const unsigned char*>(A.val + e0) + off,
-                    min(HF_BULK_PIECE, n * 8u - off), &mbar);
-      for (unsigned off = 0; off < n * 2u; off += HF_BULK_PIECE)
-        hf_bulk_g2s(reinterpret_cast<unsigned char*>(scol) + off, reinterpret_cast<const unsigned char*>(A.lcol + e0) + off,
-                    min(HF_BULK_PIECE, n * 2u - off), &mbar);
+      for (int st = 0; st < S.nstages; ++st) hf_mbar_init(&full[st], 1);
+      for (int j = 0; j < min(S.nstages, nloc); ++j) {
+        const int ch = blockIdx.x + j * G;
+        hf_issue_chunk<R>(A, ch, A.slice_ptr[ch * SPC], A.slice_ptr[(ch + 1) * SPC], smraw + (size_t)j * S.stage_bytes, S.mat_cap,
+                          S.halo_cap, x, ro, po, qo, &full[j]);
+      }
     }
   }
-  // ---- phase 1: all vector loads are issued before the control block is needed
-  double xv[RPT], rv[RPT], pv[RPT], qv[RPT];
-#pragma unroll
-  for (int t = 0; t < RPT; ++t) {
-    const int g = lo + t * HF_BLOCK + tid;
-    xv[t] = x[g];
-    rv[t] = ro[g];
-    pv[t] = po[g];
-    qv[t] = qo[g];
+  // ---- halo pipeline prologue: extents of chunks 0..2, indices of chunks 0..1, values of chunk 0
+  int hp_a = 0, nh_a = 0, hp_b = 0, nh_b = 0, hp_c = 0, nh_c = 0;
+  if (nloc > 0) {
+    hp_a = A.halo_ptr[blockIdx.x];
+    nh_a = A.halo_ptr[blockIdx.x + 1] - hp_a;
   }
-  __syncthreads();                      // control block (and the mbarrier init) visible to the CTA
+  if (nloc > 1) {
+    hp_b = A.halo_ptr[blockIdx.x + G];
+    nh_b = A.halo_ptr[blockIdx.x + G + 1] - hp_b;
+  }
+  if (nloc > 2) {
+    hp_c = A.halo_ptr[blockIdx.x + 2 * G];
+    nh_c = A.halo_ptr[blockIdx.x + 2 * G + 1] - hp_c;
+  }
+  int g_b = (tid < nh_b) ? A.halo_idx[hp_b + tid] : -1;
+  double hr = 0.0, hp = 0.0, hq = 0.0;
+  if (tid < nh_a) {
+    const int g = A.halo_idx[hp_a + tid];
+    hr = ro[g];
+    hp = po[g];
+    hq = qo[g];
+  }
+  __syncthreads();                      // control block and mbarrier inits visible to the CTA
   const int done = s_ctl_i[0], it = s_ctl_i[1];
   const double alpha = s_ctl_d[0], beta = s_ctl_d[1];
-  if (done) return;                     // uniform over the grid: thread 0 has not started a copy either
-  double l_rr = 0.0;
-#pragma unroll
-  for (int t = 0; t < RPT; ++t) {
-    const int i = t * HF_BLOCK + tid;
-    double r_new = rv[t], p_new = rv[t];
-    if (it > 0) {
-      x[lo + i] = fma(alpha, pv[t], xv[t]);
-      r_new = fma(-alpha, qv[t], rv[t]);
-      p_new = fma(beta, pv[t], r_new);
+  if (done) return;                     // uniform over the grid: no copy has been started either
+  double l_rr = 0.0, l_pq = 0.0, l_rq = 0.0, l_qq = 0.0;
+  for (int j = 0; j < nloc; ++j) {
+    const int ch = blockIdx.x + j * G;
+    const int stg = j % S.nstages;
+    const unsigned parity = (unsigned)(j / S.nstages) & 1u;
+    unsigned char* st = smraw + (size_t)stg * S.stage_bytes;
+    const double* sval = reinterpret_cast<const double*>(st);
+    double* sx = reinterpret_cast<double*>(st + (size_t)S.mat_cap * 8);
+    double* sr = sx + R;
+    double* sq = sr + R;
+    double* sp = sq + R;                // own rows, halo follows at sp[R + h]
+    const unsigned short* scol = reinterpret_cast<const unsigned short*>(sp + R + S.halo_cap);
+    const int* sptr = reinterpret_cast<const int*>(scol + S.mat_cap);
+    const int lo = ch * R;
+    // thread 0: operator extent of the chunk that will refill this stage (needed only after phase 2)
+    int nx_e0 = 0, nx_e1 = 0;
+    if (tid == 0 && j + S.nstages < nloc) {
+      const int chn = ch + S.nstages * G;
+      nx_e0 = A.slice_ptr[chn * SPC];
+      nx_e1 = A.slice_ptr[(chn + 1) * SPC];
     }
-    rn[lo + i] = r_new;
-    pn[lo + i] = p_new;
-    sp[i] = p_new;
-    sr[i] = r_new;
-    l_rr = fma(r_new, r_new, l_rr);
-  }
-  for (int h = tid; h < nh; h += HF_BLOCK) {
-    const int g = A.halo_idx[hp0 + h];
-    const double r_old = ro[g];
-    double p_new = r_old;
-    if (it > 0) p_new = fma(beta, po[g], fma(-alpha, qo[g], r_old));
-    sp[R + h] = p_new;
-  }
-  __syncthreads();                      // sp/sr complete
-  hf_mbar_wait(&mbar, 0);               // operator block has landed
-  // ---- phase 2: q = Ahat p, everything from shared memory
-  double l_pq = 0.0, l_rq = 0.0, l_qq = 0.0;
-  for (int sl = warp; s_first + sl < s_end; sl += HF_BLOCK / 32) {
-    const int base = A.slice_ptr[s_first + sl] - e0;
-    const int w = (A.slice_ptr[s_first + sl + 1] - e0 - base) >> 5;
-    const unsigned short* cp = scol + base + lane;
-    const double* vp = sval + base + lane;
-    double acc0 = 0.0, acc1 = 0.0;
-    int k = 0;
-    for (; k + 2 <= w; k += 2) {
-      acc0 = fma(vp[k * 32], sp[cp[k * 32]], acc0);
-      acc1 = fma(vp[(k + 1) * 32], sp[cp[(k + 1) * 32]], acc1);
+    hf_mbar_wait(&full[stg], parity);
+    // ---- phase 1: finish iteration n-1 on the own rows (from the stage) and on the halo (from registers)
+    if (tid < R) {
+      const double rv = sr[tid];
+      double r_new = rv, p_new = rv;
+      if (it > 0) {
+        const double pv = sp[tid];
+        x[lo + tid] = fma(alpha, pv, sx[tid]);
+        r_new = fma(-alpha, sq[tid], rv);
+        p_new = fma(beta, pv, r_new);
+      }
+      rn[lo + tid] = r_new;
+      pn[lo + tid] = p_new;
+      sp[tid] = p_new;
+      sr[tid] = r_new;
+      l_rr = fma(r_new, r_new, l_rr);
     }
-    if (k < w) acc0 = fma(vp[k * 32], sp[cp[k * 32]], acc0);
-    const double acc = acc0 + acc1;
-    const int i = sl * HF_SLICE + lane;
-    qn[lo + i] = acc;
-    l_pq = fma(sp[i], acc, l_pq);
-    l_rq = fma(sr[i], acc, l_rq);
-    l_qq = fma(acc, acc, l_qq);
+    if (tid < nh_a) sp[R + tid] = (it > 0) ? fma(beta, hp, fma(-alpha, hq, hr)) : hr;
+    for (int h = HF_IT + tid; h < nh_a; h += HF_IT) {       // oversized halos (poor node order): synchronous
+      const int g = A.halo_idx[hp_a + h];
+      const double r_old = ro[g];
+      sp[R + h] = (it > 0) ? fma(beta, po[g], fma(-alpha, qo[g], r_old)) : r_old;
+    }
+    __syncthreads();
+    // ---- advance the halo pipeline (all loads are consumed one iteration later)
+    if (g_b >= 0) {
+      hr = ro[g_b];
+      hp = po[g_b];
+      hq = qo[g_b];
+    }
+    hp_a = hp_b;
+    nh_a = nh_b;
+    g_b = (tid < nh_c) ? A.halo_idx[hp_c + tid] : -1;
+    hp_b = hp_c;
+    nh_b = nh_c;
+    if (j + 3 < nloc) {
+      hp_c = A.halo_ptr[ch + 3 * G];
+      nh_c = A.halo_ptr[ch + 3 * G + 1] - hp_c;
+    } else {
+      nh_c = 0;
+    }
+    // ---- phase 2: q = Ahat p, everything from shared memory
+    if (warp < SPC) {
+      const int e0 = sptr[0];
+      const int base = sptr[warp] - e0;
+      const int w = (sptr[warp + 1] - e0 - base) >> 5;     // 0 for the padding slices behind the last row
+      const unsigned short* cp = scol + base + lane;
+      const double* vp = sval + base + lane;
+      double acc0 = 0.0, acc1 = 0.0;
+      int k = 0;
+      for (; k + 4 <= w; k += 4) {
+        const int c0 = cp[k * 32], c1 = cp[(k + 1) * 32], c2 = cp[(k + 2) * 32], c3 = cp[(k + 3) * 32];
+        const double v0 = vp[k * 32], v1 = vp[(k + 1) * 32], v2 = vp[(k + 2) * 32], v3 = vp[(k + 3) * 32];
+        acc0 = fma(v0, sp[c0], acc0);
+        acc1 = fma(v1, sp[c1], acc1);
+        acc0 = fma(v2, sp[c2], acc0);
+        acc1 = fma(v3, sp[c3], acc1);
+      }
+      for (; k < w; ++k) acc0 = fma(vp[k * 32], sp[cp[k * 32]], acc0);
+      const double acc = acc0 + acc1;
+      const int i = warp * HF_SLICE + lane;
+      qn[lo + i] = acc;
+      l_pq = fma(sp[i], acc, l_pq);
+      l_rq = fma(sr[i], acc, l_rq);
+      l_qq = fma(acc, acc, l_qq);
+    }
+    __syncthreads();                    // the stage is free again
+    if (tid == 0 && j + S.nstages < nloc)
+      hf_issue_chunk<R>(A, ch + S.nstages * G, nx_e0, nx_e1, st, S.mat_cap, S.halo_cap, x, ro, po, qo, &full[stg]);
   }
   // ---- per-CTA partials (one barrier for the four sums), last CTA finalises the iteration
-  const int G = gridDim.x;
   {
     const double v0 = hf_warp_sum(l_rr), v1 = hf_warp_sum(l_pq), v2 = hf_warp_sum(l_rq), v3 = hf_warp_sum(l_qq);
     if (lane == 0) {
@@ -187,38 +292,42 @@ k_pcg_iter(PatchView A, int par, int mat_cap, double* __restrict__ x, double* __
     }
   }
   __syncthreads();
-  if (tid < 4) {
+  if (warp != 0) return;
+  if (lane < 4) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < HF_BLOCK / 32; ++i) t += sh4[tid][i];
-    __stcg(parts + tid * G + blockIdx.x, t);
-    __threadfence();
+    for (int i = 0; i < NW; ++i) t += sh4[lane][i];
+    __stcg(parts + lane * G + blockIdx.x, t);
   }
   __syncwarp();
-  if (tid == 0) {
+  int last = 0;
+  if (lane == 0) {
+    __threadfence();                    // partials of lanes 0..3 (same warp, ordered by __syncwarp) before the ticket
     const unsigned ticket = atomicAdd(&c->counter, 1u);
-    s_last = (ticket == (unsigned)G - 1u);
-    if (s_last) c->counter = 0u;
-    __threadfence();
+    last = (ticket == (unsigned)G - 1u);
+    if (last) {
+      c->counter = 0u;
+      __threadfence();
+    }
   }
-  __syncthreads();
-  if (!s_last) return;
-  // warp a sums quantity a over the CTAs in a fixed order
-  if (warp < 4) {
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  // lanes sum the four quantities over the CTAs in a fixed order
+  double t4[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
     double v = 0.0;
-    for (int i = lane; i < G; i += 32) v += __ldcg(parts + warp * G + i);
-    v = hf_warp_sum(v);
-    if (lane == 0) tot[warp] = v;
+    for (int i = lane; i < G; i += 32) v += __ldcg(parts + a * G + i);
+    t4[a] = hf_warp_sum(v);
   }
-  __syncthreads();
-  if (tid == 0) {
-    const double rr = tot[0];
+  if (lane == 0) {
+    const double rr = t4[0];
     c->rr = rr;
     if (!(rr > c->thr)) {               // also stops on NaN
       c->done = 1;
     } else {
-      const double al = rr / tot[1];
-      const double rr_next = fma(al * al, tot[3], fma(-2.0 * al, tot[2], rr));
+      const double al = rr / t4[1];
+      const double rr_next = fma(al * al, t4[3], fma(-2.0 * al, t4[2], rr));
       c->alpha = al;
       c->beta = fmax(rr_next, 0.0) / rr;
       c->itA = it + 1;
@@ -285,29 +394,20 @@ static const int kChunk[3] = {8, 32, 128};
 static int launch_iteration(hf_ctx* c, const SellOp& op, int par) {
   PcgWork& w = c->ws;
   const PatchView A = op.patch();
-  const size_t sm = op.iter_smem;
-  switch (op.R) {
-    case 1024:
-      k_pcg_iter<4><<<op.nchunks, HF_BLOCK, sm, c->stream>>>(A, par, op.mat_cap, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
-      break;
-    case 512:
-      k_pcg_iter<2><<<op.nchunks, HF_BLOCK, sm, c->stream>>>(A, par, op.mat_cap, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
-      break;
-    default:
-      k_pcg_iter<1><<<op.nchunks, HF_BLOCK, sm, c->stream>>>(A, par, op.mat_cap, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
-      break;
-  }
+  const IterStage S{op.mat_cap, op.halo_cap, op.nstages, (unsigned)op.stage_bytes};
+  const int grid = std::min(op.nchunks, c->sm_count);
+  if (op.R == 512)
+    k_pcg_iter<512><<<grid, HF_IT, op.iter_smem, c->stream>>>(A, par, S, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
+  else
+    k_pcg_iter<256><<<grid, HF_IT, op.iter_smem, c->stream>>>(A, par, S, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
   return HF_OK;
 }
 
 static int set_iter_smem(const SellOp& op) {
   // per function, not per operator: raise the limit right before use
   const int sm = (int)op.iter_smem;
-  if (sm > 48 * 1024) {
-    if (op.R == 1024) HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    else if (op.R == 512) HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    else HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  }
+  if (op.R == 512) HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  else HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   return HF_OK;
 }
 
@@ -331,7 +431,7 @@ static int build_chunks(hf_ctx* c, const SellOp& op) {
 int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out) {
   PcgWork& w = c->ws;
   if (!op.chunk_exec[0]) HF_TRY(build_chunks(c, op));
-  if (op.iter_smem > 48 * 1024) HF_TRY(set_iter_smem(op));
+  HF_TRY(set_iter_smem(op));
   const size_t hdr = sizeof(double) * 3 + sizeof(int) * 4;
   int launched = 0;
   // first burst: what the previous solve needed (time steps are similar), then short chunks
