@@ -11,6 +11,17 @@ variant) - no data-path collective, one final gather of the watcher histories ("
 ``value`` = DOF-timesteps/s of the whole job with the state resident in HBM, device-timed;
 ``e2e`` = the same through the C-ABI with host buffers (state upload, amplitudes in, watcher
 histories and final field out) inside the timed region.
+
+Extra objects on the JSON line:
+  roofline      dominant kernel of the timed region.  At the cfg's own size the mesh fits in
+                shared memory and the whole solve runs in ``k_pcg_persist`` (HBM traffic ~ 0), so
+                ``achieved`` is the HBM-equivalent rate: algorithmic bytes of the PCG iterations
+                it performs / its launch time.
+  roofline_1m   ``k_pcg_iter`` (streaming kernel, one launch per PCG iteration) on the >= 1 M-dof
+                refinement of ``cfgs/konopkova.yaml`` (BASELINE config #4), timed inside a real solve:
+                CUDA events around the step loop / launches, so launch gaps count against it.
+  sweep         ensemble tile of 16 (k, fwhm) variants per GPU through ``hf_ens_*`` -> sims/s.
+  cpu_baseline  the scipy sparse-LU oracle on this host (1 core), bounded sample.
 """
 import argparse
 import json
@@ -139,14 +150,46 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def kernel_roofline(solver, n, nnz, peak, peak_src, traffic=None):
-    ms_spmv, ms_upd = solver.bench_kernels(reps=30, flush_l2=True)
-    alg = 12.0 * nnz + 4.0 * n / 32 + 32.0 * n        # SpMV kernel: matrix + slice ptr + r, p_old, p_new, q
-    ach = alg / (ms_spmv * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "k_pcg_spmv", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_us": ms_spmv * 1e3,
-            "update_kernel_us": ms_upd * 1e3, "update_kernel_GBs": 48.0 * n / (ms_upd * 1e-3) / 1e9,
-            "peak_source": peak_src, "how": "CUDA events on the launching stream, 30 launches, L2 flushed between launches"}
+# algorithmic bytes of one PCG iteration: fp64 values + 16-bit local columns,
+# slice pointers, x r p q read and written once
+def iter_bytes(n, nnz):
+    return 10.0 * nnz + 4.0 * n / 32 + 64.0 * n
+
+
+def configured_solver(case, device, rtol, warm=0.0, mode=0, ordering="auto"):
+    from heatflow_b200.solver import HeatSolver
+    s = HeatSolver(device)
+    s.set_ordering(ordering)
+    s.set_mesh(case.nodes, case.tris, case.cell_tag)
+    s.set_materials(case.tags, case.kappa_t, case.rhoc_t)
+    s.set_bcs(case.bc_dofs, case.bc_value, case.gauss_slot, case.gauss_r)
+    s.build_operator(case.dt, True)
+    s.set_solver(rtol=rtol, warm=warm, mode=mode)
+    return s
+
+
+def streaming_roofline(case, device, rtol, peak, peak_src, steps, traffic=None):
+    """k_pcg_iter timed inside a solve of `steps` time steps (CUDA events around the step loop)."""
+    s = configured_solver(case, device, rtol, mode=1)
+    n, nnz = s.sizes()
+    s.set_state(np.full(n, case.ic))
+    k0 = min(10, max(0, case.num_steps - steps - 1))
+    s.run(case.amps[k0:k0 + 1], case.ic, case.coeff, [0])               # warm-up: graphs captured
+    l0 = s.stats()["launches"]
+    _, iters, _ = s.run(case.amps[k0 + 1:k0 + 1 + steps], case.ic, case.coeff, [0])
+    st = s.stats()
+    launches = st["launches"] - l0
+    us = st["run_ms"] * 1e3 / max(1, launches)
+    alg = iter_bytes(n, nnz)
+    ms_flushed, _ = s.bench_kernels(reps=20, flush_l2=True)
+    s.close()
+    ach = alg / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "k_pcg_iter", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_us": us, "launches": int(launches),
+            "pcg_iterations": int(iters.sum()), "n_dofs": n, "nnz": nnz,
+            "isolated_launch_us_l2_flushed": ms_flushed * 1e3, "peak_source": peak_src,
+            "how": f"CUDA events on the solver stream around {steps} time steps / kernels launched in between "
+                   "(every launch of the loop: per-step RHS kernels and early-exit launches after convergence included)"}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -161,13 +204,7 @@ def run_ours(args, rank, world, local_rank):
     c = build(rank)
     n = len(c.nodes)
     steps = min(args.steps, c.num_steps)
-    from heatflow_b200.solver import HeatSolver
-    s = HeatSolver(local_rank)
-    s.set_mesh(c.nodes, c.tris, c.cell_tag)
-    s.set_materials(c.tags, c.kappa_t, c.rhoc_t)
-    s.set_bcs(c.bc_dofs, c.bc_value, c.gauss_slot, c.gauss_r)
-    s.build_operator(c.dt, True)
-    s.set_solver(rtol=args.rtol, warm=args.warm_start)
+    s = configured_solver(c, local_rank, args.rtol, warm=args.warm_start)
     _, nnz = s.sizes()
     tree = cKDTree(c.nodes)
     watch = np.array([tree.query(p)[1] for p in [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0)]], dtype=np.int32)
@@ -202,12 +239,34 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     barrier()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---- sweep tile: 16 (k, fwhm) variants of config #5 per GPU through the ensemble kernels
+    sweep_ms = 0.0
+    if not args.skip_sweep:
+        from heatflow_b200 import problem as _problem
+        B = 16
+        ks = np.logspace(0.0, 2.0, 64)[(np.arange(B) + 16 * rank) % 64]
+        fw = np.logspace(-6.0, -4.0, 64)[(np.arange(B) * 5 + rank) % 64]
+        se = configured_solver(c, local_rank, args.rtol, ordering="hilbert")
+        sample_tag = int(c.tags[[m.name for m in c.mats].index("p_sample")])
+        coeffs = [_problem.gaussian_coeff(f) for f in fw]
+        se.set_state(u0)
+        se.ens_create(ks, coeffs, sample_tag)
+        se.ens_run(c.amps[20:22], c.ic, watch)                  # warm-up
+        se.ens_destroy()
+        se.set_state(u0)
+        se.ens_create(ks, coeffs, sample_tag)
+        barrier()
+        se.ens_run(c.amps[:steps], c.ic, watch)
+        sweep_ms = se.stats()["run_ms"]
+        barrier()
+        se.close()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, sweep_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gathered = [torch.zeros_like(torch.from_numpy(hist).cuda()) for _ in range(world)] if rank == 0 else None
         dist.gather(torch.from_numpy(hist).cuda(), gathered, dst=0)     # the single final gather
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, sweep_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         s.close()
         if world > 1:
@@ -215,14 +274,37 @@ def run_ours(args, rank, world, local_rank):
         return
 
     peak, peak_src = measured_peak()
-    roof = kernel_roofline(s, n, nnz, peak, peak_src)
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+    persistent = launches <= steps * 8           # one cooperative launch per solve (+ RHS / BC / sample kernels)
+    if persistent:
+        alg = iter_bytes(n, nnz) * float(iters.sum()) / steps          # per k_pcg_persist launch (= per time step)
+        us = dev_ms * 1e3 / steps
+        roof = {"bound": "hbm", "kernel": "k_pcg_persist", "achieved": alg / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                "traffic": traffic.get("k_pcg_persist"), "algorithmic_bytes_per_launch": alg, "launch_us": us,
+                "pcg_iterations_per_launch": float(iters.sum()) / steps, "peak_source": peak_src,
+                "note": "operator and vectors live in shared memory / registers for the whole solve; achieved is the "
+                        "HBM-equivalent rate of the PCG iterations performed (DRAM traffic itself is ~0, see traffic)",
+                "how": "CUDA events on the solver stream around the step loop / time steps (one launch per step)"}
+    else:
+        alg = iter_bytes(n, nnz)
+        us = dev_ms * 1e3 / max(1, launches)
+        roof = {"bound": "hbm", "kernel": "k_pcg_iter", "achieved": alg / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                "traffic": traffic.get("k_pcg_iter"), "algorithmic_bytes_per_launch": alg, "launch_us": us, "peak_source": peak_src,
+                "how": "CUDA events on the solver stream around the step loop / kernels launched"}
+    roof["frac"] = roof["achieved"] / peak
     line = {
         "metric": METRIC, "value": world * n * steps / (dev_ms * 1e-3), "unit": "DOF-timesteps/s", "n_gpus": world,
         "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD}: 1 simulation per GPU (sweep variant = rank), N={n} dofs, nnz={nnz}, "
-                               f"cfg mesh sizes, in-repo mesher; rtol={args.rtol:g}",
-                   "l2": "working set (~20 MB) is smaller than L2; kernel roofline timed with an L2 flush between launches",
+                               f"cfg mesh sizes, in-repo mesher; rtol={args.rtol:g}, warm start {args.warm_start:g}",
+                   "l2": "working set (~20 MB) is smaller than L2 and lives on chip; the >= 1 M-dof roofline run has a "
+                         "~145 MB working set (> 126 MB L2)",
                    "pcg_iterations_total": int(iters.sum()), "pcg_iterations_max": int(iters.max())},
         "e2e": {"value": world * n * steps / (e2e_ms * 1e-3), "unit": "DOF-timesteps/s",
                 "h2d_bytes_per_step": (n * 8 + steps * 8 + len(watch) * 4) / steps,
@@ -231,26 +313,17 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks.summary(),
         "roofline": roof,
     }
-    # >= 1 M-dof mesh (north_star target for the SpMV roofline): same cfg, size_scale 0.35
+    if sweep_ms > 0.0:
+        line["sweep"] = {"sims_per_s": world * 16 / (sweep_ms * 1e-3), "variants": world * 16, "batch_per_gpu": 16, "steps": steps,
+                         "dof_timesteps_per_s": world * 16 * n * steps / (sweep_ms * 1e-3),
+                         "note": "one ensemble tile per GPU, device-timed (max over ranks); the 4096-variant sweep of "
+                                 "config #5 is 256 such tiles"}
+    # >= 1 M-dof mesh (north_star target for the SpMV roofline): BASELINE config #4, konopkova cfg refined x 0.35
     if not args.skip_large:
-        cl = build(0, size_scale=0.35)
-        sl = HeatSolver(local_rank)
-        sl.set_mesh(cl.nodes, cl.tris, cl.cell_tag)
-        sl.set_materials(cl.tags, cl.kappa_t, cl.rhoc_t)
-        sl.set_bcs(cl.bc_dofs, cl.bc_value, cl.gauss_slot, cl.gauss_r)
-        sl.build_operator(cl.dt, True)
-        sl.set_solver(rtol=args.rtol)
-        sl.set_state(np.full(len(cl.nodes), cl.ic))
-        sl.run(cl.amps[20:22], cl.ic, cl.coeff, [0])
-        nl, nnzl = sl.sizes()
-        traffic_1m = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic_1m = json.load(f).get("k_pcg_spmv_1m")
-        except Exception:
-            pass
-        line["roofline_1m"] = dict(kernel_roofline(sl, nl, nnzl, peak, peak_src, traffic_1m), n_dofs=nl, nnz=nnzl)
-        sl.close()
+        from helpers import build_case
+        cl = build_case("konopkova", 0.35)
+        line["roofline_1m"] = streaming_roofline(cl, local_rank, args.rtol, peak, peak_src, steps=3,
+                                                 traffic=traffic.get("k_pcg_iter_1m"))
     # CPU baseline on this host (bounded sample)
     if not args.skip_cpu:
         cb_steps = min(20, steps)
@@ -273,9 +346,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rtol", type=float, default=1e-14)
-    ap.add_argument("--warm-start", type=float, default=0.0)
+    ap.add_argument("--warm-start", type=float, default=1.0)
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-sweep", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,37 +1,41 @@
 // heatflow_b200 - batched multi-RHS ensemble for parameter_sweep (sm_100a).
 //
 // Replaces the reference's one-process-per-parameter-set loop (parameter_sweep.py:123-192,
-// :436-438): B variants of one simulation - different sample conductivity k_s and Gaussian
-// heating width fwhm_s, same mesh, same materials otherwise - advance together.
+// :436-438): B variants of one simulation - different sample conductivity k_b and Gaussian
+// heating width fwhm_b, same mesh, same materials otherwise - advance together.
 //
-//   operator of variant s :  A0_s = base0 + k_s * S0      (two value arrays on the shared pattern)
+//   operator of variant b :  A0_b = base0 + k_b * S0      (two value arrays on the shared pattern)
 //       base0 = M(rho_c) + dt K(kappa with kappa_sample = 0),  S0 = dt K(1 on sample cells, else 0)
-//   Dirichlet rows/cols are masked on the fly (bcflag), so the same two arrays serve the RHS
-//   (un-BC'd operator, apply_lifting) and the solve (BC'd operator).
+//   Dirichlet rows are masked through the diagonal array (d = 0 there), Dirichlet columns carry a zero
+//   search direction, so the same two arrays serve the RHS (un-BC'd operator, apply_lifting) and the solve.
 //   vectors               :  [N, B] with the variant index fastest, so the gather of column j
 //                            reads B contiguous doubles and the matrix entry is shared by B lanes.
-//   thread mapping        :  one thread per (row, variant); a warp covers 32/B consecutive rows.
+//   thread mapping        :  one thread per (row, variant) pair.
 //
 // Jacobi-PCG per variant with its own alpha/beta/convergence (converged variants are frozen with
-// alpha = beta = 0), in the Jacobi-scaled space of each variant (shat_b = 1/sqrt(diag A_b)), with the
-// same one-launch-per-iteration structure as the single-simulation streaming kernel (hf_pcg.cu):
-// k_ens_iter, kernel n of a solve, on chunks of R rows x B variants (one CTA each):
-//   phase 1  x += alpha p_old shat ; r_n = r - alpha q ; p_n = r_n + beta p_old   (own rows; halo rows
-//            recomputed redundantly) ; shat * p_n -> shared memory [(R + halo), B]
-//   phase 2  q_n = shat_i sum_j (base0_ij + k_b S0_ij) (shat_j p_n,j) from shared memory with 16-bit
-//            local columns ; per-variant partials of r.r, p.q, r.q, q.q
-//   tail     last CTA: rr_n direct -> convergence / alpha_n ; rr_{n+1} by the residual identity -> beta
-// The "last CTA" adds the per-CTA partials in CTA order, so results are bit-reproducible.
+// alpha = beta = 0), written on the preconditioned residual z = D^-1 r, the search direction p and
+// w = D^-1 A p, so that the halo update needs no per-variant scaling:
+//     z_n = z - alpha w ;  p_n = z_n + beta p ;  q = A_b p_n ;  w_n = q / d
+//     r.z = sum z^2 d ;  p.Ap = sum p q ;  r.(D^-1 A p) = sum z q ;  |D^-1/2 A p|^2 = sum q^2 / d
+// One launch per iteration (k_ens_iter), same structure as the single-simulation streaming kernel
+// (hf_pcg.cu): persistent CTAs walk chunks of HF_EPAIRS/B rows x B variants; the chunk's operator
+// entries, local row pointers, 16-bit local columns and own-row vectors (x z w p d) stream into
+// shared-memory stages by TMA bulk copies; halo values go through a register pipeline; the last CTA
+// adds the per-CTA partial sums in CTA order (bit-reproducible) and sets alpha_n, beta_{n+1}, flags.
 // Algorithmic traffic per dof, iteration and variant (nnz ~ 7 / row, halo fraction h):
-//   matrix (18*nnz + 4 + 1)/B (two value arrays + 16-bit columns, shared by the B variants)
-//   vectors: read x r p q shat (40 + 32 h), write x r p q (32)          total ~ 72 + 32 h + 131/B bytes.
+//   matrix (18*nnz + 4)/B (two value arrays + 16-bit columns, shared by the B variants)
+//   vectors: read x z w p d (40 + 24 h), write x z w p (32)             total ~ 72 + 24 h + 130/B bytes.
 #include <algorithm>
 #include <cmath>
 
 #include "hf_ctx.cuh"
 
 #define HF_EB 32            // max variants per tile
-#define HF_ET 256           // threads per CTA
+#define HF_ET 256           // threads per CTA of the set-up kernels
+#define HF_ENT 512          // threads per CTA of the iteration kernel
+#define HF_EPAIRS 1024      // (row, variant) pairs per chunk: R = HF_EPAIRS / B rows
+#define HF_ERPT (HF_EPAIRS / HF_ENT)
+#define HF_EHPT 4           // halo pairs per thread carried in registers
 
 struct EnsCtrl {
   int done, it, n_active, pad;
@@ -43,19 +47,21 @@ struct EnsCtrl {
 struct EnsState {
   int B = 0, LB = 0;        // tile width (power of two) and its log2
   int nb = 0;               // real variants in the tile (<= B)
-  int grid = 0;
+  int grid = 0;             // CTAs of the set-up kernels
   int last_iters = 0;
   DevBuf<double> base0, s0;           // [nnz]
   DevBuf<double> ks, coeff;           // [B]
-  DevBuf<double> dinv, g, u, x, r, r1, p0, p1, q, q1;   // [Nalloc*B]; dinv holds shat = 1/sqrt(diag)
-  DevBuf<double> part;                // [4][max(grid, nchunks)][B]
+  DevBuf<double> dg, g, u, uprev, x, z, z1, p0, p1, w, w1;   // [Nalloc*B]; dg = diagonal of A_b (0 on Dirichlet rows)
+  bool have_prev = false;
+  DevBuf<double> part;                // [4][CTAs][B]
   // patch decomposition for the iteration kernel
-  int R = 0, nchunks = 0, halo_max = 0;
-  size_t iter_smem = 0;
+  int R = 0, nchunks = 0, halo_max = 0, halo_cap = 0, mcap = 0, nstages = 0, igrid = 0;
+  size_t stage_bytes = 0, iter_smem = 0;
   DevBuf<int> halo_ptr, halo_idx;
-  DevBuf<unsigned short> lcol;        // CSR slot order
-  DevBuf<double2> bs;                 // {base0, S0} per CSR slot
-  int mcap = 0;                       // max non-zeros of a chunk
+  DevBuf<int> rowptr_pad;             // CSR row pointers padded to whole chunks + 4
+  DevBuf<int> lc_off;                 // [nchunks+1] offsets of the chunks' column blocks (multiples of 8)
+  DevBuf<unsigned short> lcol;        // local columns, chunk blocks padded to 16 bytes
+  DevBuf<double2> bs;                 // {base0, S0} per CSR slot (16 bytes: any row range is TMA-aligned)
   DevBuf<EnsCtrl> ctrl;
   EnsCtrl* h_ctrl = nullptr;          // pinned mirror
   DevBuf<double> hist, stage;
@@ -78,7 +84,7 @@ void hf_ens_free(hf_ctx* c) {
 // ---------------------------------------------------------------------------------------
 // Sum over all threads of the CTA that share the same variant (tid & (B-1)); the result for
 // variant b lands in sh_out[b] (valid after the trailing __syncthreads()).
-template <int LB, int NT = HF_ET>
+template <int LB, int NT>
 __device__ __forceinline__ void ens_block_sum(double v, double* sh /*[NT/32][32]*/, double* sh_out /*[32]*/) {
   constexpr int B = 1 << LB;
 #pragma unroll
@@ -96,62 +102,44 @@ __device__ __forceinline__ void ens_block_sum(double v, double* sh /*[NT/32][32]
   __syncthreads();
 }
 
-// Publishes this CTA's per-variant partials and elects the last CTA to finish.  Returns true in
-// every thread of that CTA, after which part[0 .. gridDim.x) are all visible to it.
-template <int LB>
-__device__ __forceinline__ bool ens_publish(const double* sh_vals, double* part, unsigned* counter) {
-  constexpr int B = 1 << LB;
-  __shared__ int s_last;
-  if (threadIdx.x < B) {
-    __stcg(part + (size_t)blockIdx.x * B + threadIdx.x, sh_vals[threadIdx.x]);
-    __threadfence();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(counter, 1u);
-    s_last = (t == gridDim.x - 1);
-    if (s_last) *counter = 0u;
-    __threadfence();
-  }
-  __syncthreads();
-  return s_last != 0;
+__device__ __forceinline__ unsigned ens_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ens_bulk(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar,
+                                         unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          ens_smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(ens_smem_u32(bar)), "l"(policy)
+      : "memory");
 }
-
-// Fixed-order sum of the per-CTA partials, one result per variant in sh_out[b].
-template <int LB, int NT = HF_ET>
-__device__ __forceinline__ void ens_sum_parts(const double* part, int nparts, double* sh /*[NT]*/, double* sh_out) {
-  constexpr int B = 1 << LB;
-  constexpr int G = NT / B;             // groups of CTAs summed by different threads
-  const int b = threadIdx.x & (B - 1), grp = threadIdx.x >> LB;
-  double v = 0.0;
-  for (int cta = grp; cta < nparts; cta += G) v += __ldcg(part + (size_t)cta * B + b);
-  __syncthreads();
-  sh[threadIdx.x] = v;
-  __syncthreads();
-  if (threadIdx.x < B) {
-    double t = 0.0;
-    for (int k = 0; k < G; ++k) t += sh[k * B + threadIdx.x];
-    sh_out[threadIdx.x] = t;
-  }
-  __syncthreads();
+__device__ __forceinline__ void ens_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "ENS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra ENS_DONE;\n"
+      "bra ENS_WAIT;\n"
+      "ENS_DONE:\n"
+      "}\n" ::"r"(ens_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------------------
-// kernels
+// set-up kernels
 // ---------------------------------------------------------------------------------------
-// per-variant Jacobi scaling: shat = 1 / sqrt(base0_ii + k_s S0_ii), 1 on Dirichlet rows
+// per-variant diagonal d = base0_ii + k_b S0_ii; 0 marks a Dirichlet row
 template <int LB>
 __global__ void __launch_bounds__(HF_ET)
 k_ens_diag(int N, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ base0,
            const double* __restrict__ s0, const unsigned char* __restrict__ bcflag, const double* __restrict__ ks,
-           double* __restrict__ dinv, int* __restrict__ bad) {
+           double* __restrict__ dg, int* __restrict__ bad) {
   constexpr int B = 1 << LB;
   const size_t idx = (size_t)blockIdx.x * HF_ET + threadIdx.x;
   const int i = (int)(idx >> LB), b = (int)(idx & (B - 1));
   if (i >= N) return;
-  double d = 1.0;
+  double d = 0.0;
   if (!bcflag[i]) {
-    d = 0.0;
     for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
       if (col[k] == i) d = fma(ks[b], s0[k], base0[k]);
     if (!(d > 0.0)) {
@@ -159,7 +147,7 @@ k_ens_diag(int N, const int* __restrict__ rowptr, const int* __restrict__ col, c
       d = 1.0;
     }
   }
-  dinv[idx] = 1.0 / sqrt(d);
+  dg[idx] = d;
 }
 
 template <int LB>
@@ -168,6 +156,12 @@ k_ens_bcast(int N, const double* __restrict__ src, double* __restrict__ dst) {
   const size_t idx = (size_t)blockIdx.x * HF_ET + threadIdx.x;
   const int i = (int)(idx >> LB);
   if (i < N) dst[idx] = src[i];
+}
+
+// {base0, S0} interleaved per CSR slot
+__global__ void k_ens_pack(long long nnz, const double* __restrict__ base0, const double* __restrict__ s0, double2* __restrict__ bs) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nnz) bs[k] = make_double2(base0[k], s0[k]);
 }
 
 // g_jb = (amp - t_ic) exp(coeff_b r_j^2) + t_ic on the Gaussian-profile dofs (bc.py:128-137,
@@ -182,25 +176,26 @@ __global__ void k_ens_gauss(int n, const int* __restrict__ dof, const double* __
 }
 
 // assemble_vector + apply_lifting + set_bc + initial residual for all variants:
-//   free row i : rhat = shat_i ((M u)_i - (A0_s x0)_i) with x0 = u on free columns, g on Dirichlet columns
-//   bc row i   : x = g, rhat = 0
+//   free row i : z = ((M u)_i - (A0_b x0)_i) / d_i with x0 = u on free columns, g on Dirichlet columns
+//   bc row i   : x = g, z = 0
 template <int LB>
 __global__ void __launch_bounds__(HF_ET)
 k_ens_init(int N, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ valM,
            const double* __restrict__ base0, const double* __restrict__ s0, const unsigned char* __restrict__ bcflag,
            const double* __restrict__ ks, const double* __restrict__ g, const double* __restrict__ u,
-           const double* __restrict__ shat, double* __restrict__ x, double* __restrict__ r,
-           double* __restrict__ part, EnsCtrl* __restrict__ c, double rtol) {
+           const double* __restrict__ uprev, double warm, const double* __restrict__ dg, double* __restrict__ x,
+           double* __restrict__ z, double* __restrict__ part, EnsCtrl* __restrict__ c, double rtol) {
   constexpr int B = 1 << LB;
   __shared__ double sh[HF_ET];
   __shared__ double s_bn[HF_EB];
+  __shared__ int s_last;
   const int b = threadIdx.x & (B - 1);
   const double kb = ks[b];
   const size_t total = (size_t)N << LB;
   double l_bn = 0.0;
   for (size_t idx = (size_t)blockIdx.x * HF_ET + threadIdx.x; idx < total; idx += (size_t)gridDim.x * HF_ET) {
     const int i = (int)(idx >> LB);
-    double xv, rv = 0.0;
+    double xv, zv = 0.0;
     if (bcflag[i]) {
       xv = g[idx];
     } else {
@@ -215,83 +210,122 @@ k_ens_init(int N, const int* __restrict__ rowptr, const int* __restrict__ col, c
           t2 = fma(a, gj, t2);
           t3 = fma(a, gj, t3);
         } else {
-          t2 = fma(a, uj, t2);
+          t2 = fma(a, (warm != 0.0) ? fma(warm, uj - uprev[((size_t)j << LB) + b], uj) : uj, t2);
         }
       }
-      const double si = shat[idx];
-      xv = u[idx];
-      rv = (t1 - t2) * si;
-      const double bh = (t1 - t3) * si;
-      l_bn = fma(bh, bh, l_bn);
+      const double di = 1.0 / dg[idx];
+      xv = (warm != 0.0) ? fma(warm, u[idx] - uprev[idx], u[idx]) : u[idx];
+      zv = (t1 - t2) * di;
+      const double bi = t1 - t3;
+      l_bn = fma(bi * di, bi, l_bn);
     }
     x[idx] = xv;
-    r[idx] = rv;
+    z[idx] = zv;
   }
-  ens_block_sum<LB>(l_bn, sh, s_bn);
-  if (ens_publish<LB>(s_bn, part, &c->counter[0])) {
-    ens_sum_parts<LB>(part, gridDim.x, sh, s_bn);
-    if (threadIdx.x < B) {
-      c->thr[threadIdx.x] = rtol * rtol * s_bn[threadIdx.x];
-      c->bn[threadIdx.x] = s_bn[threadIdx.x];
-      c->rz[threadIdx.x] = 0.0;
-      c->alpha[threadIdx.x] = 0.0;
-      c->beta[threadIdx.x] = 0.0;
-      c->active[threadIdx.x] = 1;
-    }
-    if (threadIdx.x == 0) {
-      c->n_active = B;
-      c->done = 0;
-      c->it = 0;
-    }
+  ens_block_sum<LB, HF_ET>(l_bn, sh, s_bn);
+  if (threadIdx.x < B) {
+    __stcg(part + (size_t)blockIdx.x * B + threadIdx.x, s_bn[threadIdx.x]);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(&c->counter[0], 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) c->counter[0] = 0u;
+    __threadfence();
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x < B) {
+    double bn = 0.0;
+    for (unsigned cta = 0; cta < gridDim.x; ++cta) bn += __ldcg(part + (size_t)cta * B + threadIdx.x);
+    c->thr[threadIdx.x] = rtol * rtol * bn;
+    c->bn[threadIdx.x] = bn;
+    c->rz[threadIdx.x] = 0.0;
+    c->alpha[threadIdx.x] = 0.0;
+    c->beta[threadIdx.x] = 0.0;
+    c->active[threadIdx.x] = 1;
+  }
+  if (threadIdx.x == 0) {
+    c->n_active = B;
+    c->done = 0;
+    c->it = 0;
+    c->counter[1] = 0u;
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// iteration kernel
+// ---------------------------------------------------------------------------------------
 struct EnsPatch {
-  int R, nchunks, mcap;                      // rows per chunk, chunks, max non-zeros of a chunk
+  int nchunks, mcap, halo_cap, nstages;
+  unsigned stage_bytes;
   const int* __restrict__ halo_ptr;
   const int* __restrict__ halo_idx;
-  const unsigned short* __restrict__ lcol;   // CSR slot order
-  const double2* __restrict__ bs;            // {base0, S0} per CSR slot
+  const int* __restrict__ rowptr_pad;
+  const int* __restrict__ lc_off;
+  const unsigned short* __restrict__ lcol;
+  const double2* __restrict__ bs;
 };
 
-#define HF_EPAIRS 2048      // (row, variant) pairs per CTA: R = HF_EPAIRS / B rows
-#define HF_ENT 512          // threads per CTA of the iteration kernel
-#define HF_ERPT (HF_EPAIRS / HF_ENT)
-
-__device__ __forceinline__ unsigned ens_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
+// Stage layout (bytes, every block a multiple of 16):
+//   bs[mcap] double2 | x[EP] | z[EP] | w[EP] | d[EP] | p[EP] | halo p[halo_cap*B] | lcol[mcap] u16 | rowptr[R+4] i32
 template <int LB>
-__global__ void __launch_bounds__(HF_ENT, 2)
-k_ens_iter(int N, EnsPatch P, int par, const int* __restrict__ rowptr, const unsigned char* __restrict__ bcflag,
-           const double* __restrict__ ks, const double* __restrict__ shat, double* __restrict__ x,
-           double* __restrict__ rb0, double* __restrict__ rb1, double* __restrict__ pb0, double* __restrict__ pb1,
-           double* __restrict__ qb0, double* __restrict__ qb1, double* __restrict__ part, EnsCtrl* __restrict__ c) {
+__device__ __forceinline__ void ens_issue_chunk(const EnsPatch& P, int ch, int k0, int k1, int lc0, unsigned char* st,
+                                                const double* x, const double* zo, const double* wo, const double* dg,
+                                                const double* po, unsigned long long* bar) {
   constexpr int B = 1 << LB;
   constexpr int R = HF_EPAIRS / B;
+  constexpr unsigned vb = HF_EPAIRS * 8u;
+  unsigned char* sx = st + (size_t)P.mcap * 16;
+  unsigned char* slc = sx + 5 * (size_t)vb + (size_t)P.halo_cap * B * 8;
+  unsigned char* srow = slc + (size_t)P.mcap * 2;
+  const unsigned n = (unsigned)(k1 - k0);
+  const unsigned ncol = (n + 7u) & ~7u;
+  unsigned long long keep;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was last touched by ordinary loads/stores
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ens_smem_u32(bar)),
+               "r"(n * 16u + ncol * 2u + 5u * vb + (R + 4) * 4u)
+               : "memory");
+  const size_t lo = (size_t)ch * HF_EPAIRS;
+  ens_bulk(sx, x + lo, vb, bar, keep);
+  ens_bulk(sx + vb, zo + lo, vb, bar, keep);
+  ens_bulk(sx + 2 * vb, wo + lo, vb, bar, keep);
+  ens_bulk(sx + 3 * vb, dg + lo, vb, bar, keep);
+  ens_bulk(sx + 4 * vb, po + lo, vb, bar, keep);
+  ens_bulk(srow, P.rowptr_pad + (size_t)ch * R, (R + 4) * 4u, bar, keep);
+  if (ncol) ens_bulk(slc, P.lcol + lc0, ncol * 2u, bar, keep);
+  for (unsigned off = 0; off < n * 16u; off += 16384u)
+    ens_bulk(st + off, reinterpret_cast<const unsigned char*>(P.bs + k0) + off, min(16384u, n * 16u - off), bar, keep);
+}
+
+template <int LB>
+__global__ void __launch_bounds__(HF_ENT, 1)
+k_ens_iter(EnsPatch P, int par, const double* __restrict__ ks, const double* __restrict__ dg, double* __restrict__ x,
+           double* __restrict__ zb0, double* __restrict__ zb1, double* __restrict__ pb0, double* __restrict__ pb1,
+           double* __restrict__ wb0, double* __restrict__ wb1, double* __restrict__ part, EnsCtrl* __restrict__ c) {
+  constexpr int B = 1 << LB;
+  constexpr int R = HF_EPAIRS / B;
+  constexpr int NW = HF_ENT / 32;
   extern __shared__ __align__(128) unsigned char smraw[];
-  double2* sbs = reinterpret_cast<double2*>(smraw);                 // [mcap] {base0, S0} of the chunk's rows
-  double* sp = reinterpret_cast<double*>(sbs + P.mcap);              // shat * p_n, [(R + nh), B]
-  __shared__ double sh[HF_ENT];
+  __shared__ double sh[NW * 32];
   __shared__ double s_tot[4][HF_EB];
   __shared__ double s_al[HF_EB], s_be[HF_EB];
   __shared__ int s_ctl[2];
-  __shared__ int srow[HF_EPAIRS / 4 + 1];                           // chunk-local row pointers (R + 1 <= 513 used)
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long full[4];
   const int tid = threadIdx.x;
   const int b = tid & (B - 1);
-  const int lo = blockIdx.x * R;
-  const int hi = min(lo + R, N);
-  const int hp0 = P.halo_ptr[blockIdx.x], nh = P.halo_ptr[blockIdx.x + 1] - hp0;
-  unsigned short* slc = reinterpret_cast<unsigned short*>(sp + ((size_t)(R + nh) << LB));   // [mcap] local columns
-  const double* __restrict__ ro = par ? rb1 : rb0;
+  const int G = gridDim.x;
+  const double* __restrict__ zo = par ? zb1 : zb0;
   const double* __restrict__ po = par ? pb1 : pb0;
-  const double* __restrict__ qo = par ? qb1 : qb0;
-  double* __restrict__ rn = par ? rb0 : rb1;
+  const double* __restrict__ wo = par ? wb1 : wb0;
+  double* __restrict__ zn = par ? zb0 : zb1;
   double* __restrict__ pn = par ? pb0 : pb1;
-  double* __restrict__ qn = par ? qb0 : qb1;
-  const int k0 = rowptr[lo < N ? lo : N], k1 = rowptr[hi];
-  // ---- thread 0: the chunk's operator entries -> shared memory by TMA bulk copy
-  if (tid < B) {                        // ONE reader per CTA and variant: the whole grid polls these L2 lines
+  double* __restrict__ wn = par ? wb0 : wb1;
+  const int nloc = (P.nchunks - (int)blockIdx.x + G - 1) / G;
+  // ---- control block: ONE reader per CTA and variant (the whole grid polls these L2 lines)
+  if (tid < B) {
     s_al[tid] = *(volatile double*)&c->alpha[tid];
     s_be[tid] = *(volatile double*)&c->beta[tid];
   }
@@ -300,123 +334,214 @@ k_ens_iter(int N, EnsPatch P, int par, const int* __restrict__ rowptr, const uns
     s_ctl[0] = d;
     s_ctl[1] = *(volatile int*)&c->it;
     if (d == 0) {
-      const unsigned bytes = (unsigned)(k1 - k0) * 16u;
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ens_smem_u32(&mbar)) : "memory");
+      for (int st = 0; st < P.nstages; ++st) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ens_smem_u32(&full[st])) : "memory");
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ens_smem_u32(&mbar)), "r"(bytes) : "memory");
-      for (unsigned off = 0; off < bytes; off += 16384u)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         ens_smem_u32(reinterpret_cast<unsigned char*>(sbs) + off)),
-                     "l"(reinterpret_cast<const unsigned char*>(P.bs + k0) + off), "r"(min(16384u, bytes - off)),
-                     "r"(ens_smem_u32(&mbar))
-                     : "memory");
+      int e0[4], e1[4], el[4];          // all extents first: one round trip instead of one per stage
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = min((int)blockIdx.x + j * G, P.nchunks - 1);
+        e0[j] = P.rowptr_pad[ch * R];
+        e1[j] = P.rowptr_pad[(ch + 1) * R];
+        el[j] = P.lc_off[ch];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < min(P.nstages, nloc))
+          ens_issue_chunk<LB>(P, blockIdx.x + j * G, e0[j], e1[j], el[j], smraw + (size_t)j * P.stage_bytes, x, zo, wo, dg, po,
+                              &full[j]);
     }
   }
-  const size_t g0 = ((size_t)lo << LB) + tid;          // this thread's first pair; pairs are HF_ENT apart
-  // ---- phase 1 (own rows): loads first, control block afterwards
-  double xv[HF_ERPT], rv[HF_ERPT], pv[HF_ERPT], qv[HF_ERPT], sv[HF_ERPT];
-#pragma unroll
-  for (int t = 0; t < HF_ERPT; ++t) {
-    const size_t g = g0 + (size_t)t * HF_ENT;
-    xv[t] = x[g];
-    rv[t] = ro[g];
-    pv[t] = po[g];
-    qv[t] = qo[g];
-    sv[t] = shat[g];
+  // ---- halo pipeline prologue: extents of chunks 0..2, node indices of chunks 0..1, values of chunk 0
+  // (list begin, list end) per chunk; the subtraction happens where the count is used, one iteration after
+  // the loads were issued, so that no load latency is exposed inside the chunk loop
+  int hp_a = 0, he_a = 0, hp_b = 0, he_b = 0, hp_c = 0, he_c = 0;
+  if (nloc > 0) {
+    hp_a = P.halo_ptr[blockIdx.x];
+    he_a = P.halo_ptr[blockIdx.x + 1];
   }
-  for (int k = k0 + tid; k < k1; k += HF_ENT) slc[k - k0] = P.lcol[k];
-  for (int i = tid; i <= R; i += HF_ENT) srow[i] = rowptr[min(lo + i, N)] - k0;
+  if (nloc > 1) {
+    hp_b = P.halo_ptr[blockIdx.x + G];
+    he_b = P.halo_ptr[blockIdx.x + G + 1];
+  }
+  if (nloc > 2) {
+    hp_c = P.halo_ptr[blockIdx.x + 2 * G];
+    he_c = P.halo_ptr[blockIdx.x + 2 * G + 1];
+  }
+  const int nh_b0 = he_b - hp_b;
+  int nh_a = he_a - hp_a;
+  int g_b[HF_EHPT];
+  double hz[HF_EHPT], hpv[HF_EHPT], hw[HF_EHPT];
+#pragma unroll
+  for (int t = 0; t < HF_EHPT; ++t) {
+    const int h = (t * HF_ENT + tid) >> LB;
+    g_b[t] = (h < nh_b0) ? P.halo_idx[hp_b + h] : -1;
+    hz[t] = hpv[t] = hw[t] = 0.0;
+    if (h < nh_a) {
+      const size_t g = ((size_t)P.halo_idx[hp_a + h] << LB) + b;
+      hz[t] = zo[g];
+      hpv[t] = po[g];
+      hw[t] = wo[g];
+    }
+  }
   const double kb = ks[b];
-  __syncthreads();                      // control block (and the mbarrier init) visible to the CTA
+  __syncthreads();                      // control block and mbarrier inits visible to the CTA
   const int done = s_ctl[0], it = s_ctl[1];
   const double alpha = s_al[b], beta = s_be[b];
   if (done) return;
-  double l_rr = 0.0;
+  double l_rr = 0.0, l_pq = 0.0, l_rq = 0.0, l_qq = 0.0;
+  for (int j = 0; j < nloc; ++j) {
+    const int ch = blockIdx.x + j * G;
+    const int stg = j % P.nstages;
+    const unsigned parity = (unsigned)(j / P.nstages) & 1u;
+    unsigned char* st = smraw + (size_t)stg * P.stage_bytes;
+    const double2* sbs = reinterpret_cast<const double2*>(st);
+    double* sx = reinterpret_cast<double*>(st + (size_t)P.mcap * 16);
+    double* sz = sx + HF_EPAIRS;
+    double* sw = sz + HF_EPAIRS;
+    double* sd = sw + HF_EPAIRS;
+    double* sp = sd + HF_EPAIRS;        // own pairs, halo pairs follow at sp[HF_EPAIRS + ...]
+    const unsigned short* slc = reinterpret_cast<const unsigned short*>(sp + HF_EPAIRS + (size_t)P.halo_cap * B);
+    const int* srow = reinterpret_cast<const int*>(slc + P.mcap);
+    const size_t g0 = (size_t)ch * HF_EPAIRS;
+    // thread 0: extents of the chunk that will refill this stage (needed only after phase 2)
+    int nx_k0 = 0, nx_k1 = 0, nx_lc = 0;
+    if (tid == 0 && j + P.nstages < nloc) {
+      const int chn = ch + P.nstages * G;
+      nx_k0 = P.rowptr_pad[chn * R];
+      nx_k1 = P.rowptr_pad[(chn + 1) * R];
+      nx_lc = P.lc_off[chn];
+    }
+    ens_mbar_wait(&full[stg], parity);
+    // ---- phase 1: finish iteration n-1 on the own pairs (from the stage) and the halo pairs (registers)
+    double dinv[HF_ERPT];
 #pragma unroll
-  for (int t = 0; t < HF_ERPT; ++t) {
-    const size_t g = g0 + (size_t)t * HF_ENT;
-    if (it > 0) {
-      if (alpha != 0.0) x[g] = fma(alpha * sv[t], pv[t], xv[t]);
-      rv[t] = fma(-alpha, qv[t], rv[t]);
-      pv[t] = fma(beta, pv[t], rv[t]);
+    for (int t = 0; t < HF_ERPT; ++t) {
+      const int i = t * HF_ENT + tid;
+      const double d = sd[i];
+      dinv[t] = (d > 0.0) ? __drcp_rn(d) : 0.0;
+      double z_new = sz[i], p_new = z_new;
+      if (it > 0) {
+        const double pv = sp[i];
+        if (alpha != 0.0) x[g0 + i] = fma(alpha, pv, sx[i]);
+        z_new = fma(-alpha, sw[i], z_new);
+        p_new = fma(beta, pv, z_new);
+      }
+      zn[g0 + i] = z_new;
+      pn[g0 + i] = p_new;
+      sp[i] = p_new;
+      sz[i] = z_new;
+      l_rr = fma(z_new * d, z_new, l_rr);
+    }
+#pragma unroll
+    for (int t = 0; t < HF_EHPT; ++t) {
+      const int hidx = t * HF_ENT + tid;
+      if ((hidx >> LB) < nh_a) sp[HF_EPAIRS + hidx] = (it > 0) ? fma(beta, hpv[t], fma(-alpha, hw[t], hz[t])) : hz[t];
+    }
+    for (int hidx = HF_EHPT * HF_ENT + tid; (hidx >> LB) < nh_a; hidx += HF_ENT) {   // oversized halos: synchronous
+      const size_t g = ((size_t)P.halo_idx[hp_a + (hidx >> LB)] << LB) + b;
+      const double z_old = zo[g];
+      sp[HF_EPAIRS + hidx] = (it > 0) ? fma(beta, po[g], fma(-alpha, wo[g], z_old)) : z_old;
+    }
+    __syncthreads();
+    // ---- advance the halo pipeline (loads are consumed one iteration later)
+#pragma unroll
+    for (int t = 0; t < HF_EHPT; ++t) {
+      if (g_b[t] >= 0) {
+        const size_t g = ((size_t)g_b[t] << LB) + b;
+        hz[t] = zo[g];
+        hpv[t] = po[g];
+        hw[t] = wo[g];
+      }
+      const int h = (t * HF_ENT + tid) >> LB;
+      g_b[t] = (h < he_c - hp_c) ? P.halo_idx[hp_c + h] : -1;
+    }
+    hp_a = hp_b;
+    nh_a = he_b - hp_b;
+    hp_b = hp_c;
+    he_b = he_c;
+    if (j + 3 < nloc) {
+      hp_c = P.halo_ptr[ch + 3 * G];
+      he_c = P.halo_ptr[ch + 3 * G + 1];
     } else {
-      pv[t] = rv[t];
+      hp_c = he_c = 0;
     }
-    rn[g] = rv[t];
-    pn[g] = pv[t];
-    sp[t * HF_ENT + tid] = sv[t] * pv[t];
-    l_rr = fma(rv[t], rv[t], l_rr);
-  }
-  // halo rows: same update, result only in shared memory
-  for (int hidx = tid; hidx < (nh << LB); hidx += HF_ENT) {
-    const size_t g = ((size_t)P.halo_idx[hp0 + (hidx >> LB)] << LB) + b;
-    const double r_old = ro[g];
-    double p_new = r_old;
-    if (it > 0) p_new = fma(beta, po[g], fma(-alpha, qo[g], r_old));
-    sp[(R << LB) + hidx] = shat[g] * p_new;
-  }
-  __syncthreads();                      // sp, slc, srow complete
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "ENS_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-      "@p bra ENS_DONE;\n"
-      "bra ENS_WAIT;\n"
-      "ENS_DONE:\n"
-      "}\n" ::"r"(ens_smem_u32(&mbar))
-      : "memory");
-  // ---- phase 2: q = shat_i * sum_j (base0 + k_b S0)_ij * sp_j, all operands in shared memory
-  double l_pq = 0.0, l_rq = 0.0, l_qq = 0.0;
+    // ---- phase 2: q = sum_j (base0 + k_b S0)_ij p_j, everything from shared memory; w = q / d
+    const int k00 = srow[0];
 #pragma unroll
-  for (int t = 0; t < HF_ERPT; ++t) {
-    const int il = (t * HF_ENT + tid) >> LB;
-    const int i = lo + il;
-    double acc = 0.0;
-    if (i < N && !bcflag[i]) {
-      const int ka = srow[il], kz = srow[il + 1];
-      double a0 = 0.0, a1 = 0.0;
-      int k = ka;
-      for (; k + 2 <= kz; k += 2) {
-        const double2 m0 = sbs[k], m1 = sbs[k + 1];
-        a0 = fma(fma(kb, m0.y, m0.x), sp[((int)slc[k] << LB) + b], a0);
-        a1 = fma(fma(kb, m1.y, m1.x), sp[((int)slc[k + 1] << LB) + b], a1);
+    for (int t = 0; t < HF_ERPT; ++t) {
+      const int i = t * HF_ENT + tid;
+      const int il = i >> LB;
+      double q = 0.0;
+      if (dinv[t] != 0.0) {
+        const int ka = srow[il] - k00, kz = srow[il + 1] - k00;
+        double a0 = 0.0, a1 = 0.0;
+        int k = ka;
+        for (; k + 2 <= kz; k += 2) {
+          const double2 m0 = sbs[k], m1 = sbs[k + 1];
+          const int c0 = slc[k], c1 = slc[k + 1];
+          a0 = fma(fma(kb, m0.y, m0.x), sp[(c0 << LB) + b], a0);
+          a1 = fma(fma(kb, m1.y, m1.x), sp[(c1 << LB) + b], a1);
+        }
+        if (k < kz) {
+          const double2 m0 = sbs[k];
+          a0 = fma(fma(kb, m0.y, m0.x), sp[((int)slc[k] << LB) + b], a0);
+        }
+        q = a0 + a1;
       }
-      if (k < kz) {
-        const double2 m0 = sbs[k];
-        a0 = fma(fma(kb, m0.y, m0.x), sp[((int)slc[k] << LB) + b], a0);
-      }
-      acc = (a0 + a1) * sv[t];
+      wn[g0 + i] = q * dinv[t];
+      l_pq = fma(sp[i], q, l_pq);
+      l_rq = fma(sz[i], q, l_rq);
+      l_qq = fma(q * dinv[t], q, l_qq);
     }
-    qn[g0 + (size_t)t * HF_ENT] = acc;
-    l_pq = fma(pv[t], acc, l_pq);
-    l_rq = fma(rv[t], acc, l_rq);
-    l_qq = fma(acc, acc, l_qq);
+    __syncthreads();                    // the stage is free again
+    if (tid == 0 && j + P.nstages < nloc)
+      ens_issue_chunk<LB>(P, ch + P.nstages * G, nx_k0, nx_k1, nx_lc, st, x, zo, wo, dg, po, &full[stg]);
   }
   // ---- per-CTA, per-variant partials; the last CTA finalises the iteration
-  const size_t GB = (size_t)gridDim.x * B;
+  const size_t GB = (size_t)G * B;
   ens_block_sum<LB, HF_ENT>(l_rr, sh, s_tot[0]);
   ens_block_sum<LB, HF_ENT>(l_pq, sh, s_tot[1]);
   ens_block_sum<LB, HF_ENT>(l_rq, sh, s_tot[2]);
   ens_block_sum<LB, HF_ENT>(l_qq, sh, s_tot[3]);
+  if (tid >= 32) return;
   if (tid < B) {
 #pragma unroll
-    for (int a = 1; a < 4; ++a) __stcg(part + a * GB + (size_t)blockIdx.x * B + tid, s_tot[a][tid]);
+    for (int a = 0; a < 4; ++a) __stcg(part + a * GB + (size_t)blockIdx.x * B + tid, s_tot[a][tid]);
+    __threadfence();
   }
-  if (!ens_publish<LB>(s_tot[0], part, &c->counter[1])) return;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) ens_sum_parts<LB, HF_ENT>(part + a * GB, gridDim.x, sh, s_tot[a]);
+  __syncwarp();
+  int last = 0;
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(&c->counter[1], 1u);
+    last = (ticket == (unsigned)G - 1u);
+    if (last) {
+      c->counter[1] = 0u;
+      __threadfence();
+    }
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  int act = 0;
   if (tid < B) {
-    const double rr = s_tot[0][tid];
+    double t4[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      double v = 0.0;
+      for (int cta = 0; cta < G; ++cta) v += __ldcg(part + a * GB + (size_t)cta * B + tid);   // fixed order
+      t4[a] = v;
+    }
+    const double rr = t4[0];
     c->rz[tid] = rr;
     double al = 0.0, be = 0.0;
-    int act = c->active[tid];
+    act = c->active[tid];
     if (act) {
       if (!(rr > c->thr[tid])) {
-        act = 0;                          // frozen from now on: x, r stay, p = r
+        act = 0;                          // frozen from now on: x, z stay, p = z
       } else {
-        al = rr / s_tot[1][tid];
-        const double rr_next = fma(al * al, s_tot[3][tid], fma(-2.0 * al, s_tot[2][tid], rr));
+        al = rr / t4[1];
+        const double rr_next = fma(al * al, t4[3], fma(-2.0 * al, t4[2], rr));
         be = fmax(rr_next, 0.0) / rr;
       }
     }
@@ -424,20 +549,12 @@ k_ens_iter(int N, EnsPatch P, int par, const int* __restrict__ rowptr, const uns
     c->beta[tid] = be;
     c->active[tid] = act;
   }
-  __syncthreads();
+  const unsigned any = __ballot_sync(0xffffffffu, act != 0);
   if (tid == 0) {
-    int na = 0;
-    for (int k = 0; k < B; ++k) na += c->active[k];
-    c->n_active = na;
-    if (na == 0) c->done = 1;
+    c->n_active = __popc(any);
+    if (any == 0u) c->done = 1;
     else c->it = it + 1;
   }
-}
-
-// {base0, S0} interleaved per CSR slot (16 bytes per entry: any row range is TMA-aligned)
-__global__ void k_ens_pack(long long nnz, const double* __restrict__ base0, const double* __restrict__ s0, double2* __restrict__ bs) {
-  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nnz) bs[k] = make_double2(base0[k], s0[k]);
 }
 
 template <int LB>
@@ -469,7 +586,7 @@ __global__ void k_ens_transpose(int N, const int* __restrict__ rank, const doubl
     default: { constexpr int LB = 5; __VA_ARGS__; } break;     \
   }
 
-// kappa table with the sample material replaced by `k_sample_value`, others scaled by `others`
+// assemble fm * M(rho_c) + K(f_others * kappa on non-sample cells, f_sample on sample cells)
 static int ens_assemble(hf_ctx* c, int sample_tag, double fm, double f_others, double f_sample, double* out) {
   const int nt = (int)c->mat_tags.size();
   std::vector<double> cm_t(nt), ck_t(nt);
@@ -508,13 +625,13 @@ extern "C" int hf_ens_create(hf_ctx* c, int32_t batch, const double* k_sample, c
   EnsState* e = new EnsState();
   c->ens = e;
   e->nb = batch;
-  e->LB = 2;                            // tiles of fewer than 4 variants are padded: chunks stay <= 512 rows
+  e->LB = 2;                            // tiles of fewer than 4 variants are padded
   while ((1 << e->LB) < batch) ++e->LB;
   e->B = 1 << e->LB;
   const int B = e->B, N = c->N;
   e->R = HF_EPAIRS / B;
   e->nchunks = (N + e->R - 1) / e->R;
-  const size_t nb = (size_t)e->nchunks * e->R * B;      // rows padded to whole chunks (padding stays zero)
+  const size_t nb = (size_t)e->nchunks * HF_EPAIRS;      // rows padded to whole chunks (padding stays zero)
   // pad the tile by repeating the last variant
   std::vector<double> ks(B), cf(B);
   for (int s = 0; s < B; ++s) {
@@ -527,42 +644,60 @@ extern "C" int hf_ens_create(hf_ctx* c, int32_t batch, const double* k_sample, c
   HF_TRY(e->s0.alloc(c->nnz, c->stream));
   HF_TRY(ens_assemble(c, sample_tag, 1.0, c->dt, 0.0, e->base0.p));
   HF_TRY(ens_assemble(c, sample_tag, 0.0, 0.0, c->dt, e->s0.p));
-  for (DevBuf<double>* v : {&e->dinv, &e->g, &e->u, &e->x, &e->r, &e->r1, &e->p0, &e->p1, &e->q, &e->q1})
+  for (DevBuf<double>* v : {&e->dg, &e->g, &e->u, &e->uprev, &e->x, &e->z, &e->z1, &e->p0, &e->p1, &e->w, &e->w1})
     HF_TRY(v->alloc(nb, c->stream));
   const size_t blocks = ((size_t)N * B + HF_ET - 1) / HF_ET;
   e->grid = (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)c->sm_count * 8));
-  HF_TRY(e->part.alloc((size_t)4 * std::max(e->grid, e->nchunks) * B, c->stream));
+  e->igrid = std::min(e->nchunks, c->sm_count);
+  HF_TRY(e->part.alloc((size_t)4 * std::max(e->grid, e->igrid) * B, c->stream));
+  // ---- patch decomposition: halo lists, chunk-padded local columns, padded row pointers
   {
     std::vector<int> hptr, hidx;
     std::vector<unsigned short> lcol;
     HF_TRY(hf_build_patches(c, e->R, hptr, hidx, lcol, &e->halo_max));
     if (hidx.empty()) hidx.push_back(0);
-    HF_TRY(e->halo_ptr.upload(hptr.data(), hptr.size(), c->stream));
-    HF_TRY(e->halo_idx.upload(hidx.data(), hidx.size(), c->stream));
-    HF_TRY(e->lcol.upload(lcol.data(), lcol.size(), c->stream));
+    std::vector<int> lc_off(e->nchunks + 1, 0), rp((size_t)e->nchunks * e->R + 5, (int)c->nnz);
+    std::copy(c->h_rowptr.begin(), c->h_rowptr.end(), rp.begin());
     for (int ch = 0; ch < e->nchunks; ++ch) {
       const int lo = ch * e->R, hi = std::min(lo + e->R, N);
-      e->mcap = std::max(e->mcap, c->h_rowptr[hi] - c->h_rowptr[lo]);
+      const int n = c->h_rowptr[hi] - c->h_rowptr[lo];
+      e->mcap = std::max(e->mcap, n);
+      lc_off[ch + 1] = lc_off[ch] + ((n + 7) & ~7);
     }
     e->mcap = (e->mcap + 7) & ~7;
-    HF_TRY(e->bs.alloc(c->nnz, c->stream));
+    std::vector<unsigned short> lpad((size_t)lc_off[e->nchunks] + 8, 0);
+    for (int ch = 0; ch < e->nchunks; ++ch) {
+      const int lo = ch * e->R, hi = std::min(lo + e->R, N);
+      std::copy(lcol.begin() + c->h_rowptr[lo], lcol.begin() + c->h_rowptr[hi], lpad.begin() + lc_off[ch]);
+    }
+    HF_TRY(e->halo_ptr.upload(hptr.data(), hptr.size(), c->stream));
+    HF_TRY(e->halo_idx.upload(hidx.data(), hidx.size(), c->stream));
+    HF_TRY(e->lcol.upload(lpad.data(), lpad.size(), c->stream));
+    HF_TRY(e->lc_off.upload(lc_off.data(), lc_off.size(), c->stream));
+    HF_TRY(e->rowptr_pad.upload(rp.data(), rp.size(), c->stream));
+    HF_TRY(e->bs.alloc(c->nnz + 1, c->stream));
     k_ens_pack<<<(unsigned)((c->nnz + 255) / 256), 256, 0, c->stream>>>(c->nnz, e->base0.p, e->s0.p, e->bs.p);
     HF_CUDA(cudaGetLastError());
-    // {base0,S0} block + shat*p (own + halo rows, B variants) + 16-bit local columns
-    e->iter_smem = (size_t)e->mcap * 16 + sizeof(double) * (size_t)(e->R + e->halo_max) * B + (size_t)e->mcap * 2 + 16;
+    e->halo_cap = (e->halo_max + 1) & ~1;
+    e->stage_bytes = ((size_t)e->mcap * 18 + sizeof(double) * ((size_t)5 * HF_EPAIRS + (size_t)e->halo_cap * B) + 4 * (e->R + 4) + 127) &
+                     ~(size_t)127;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
-    if (e->iter_smem + 24 * 1024 > (size_t)max_smem)
+    const size_t avail = (size_t)max_smem - 8 * 1024;    // static shared memory of the kernel
+    e->nstages = (int)std::min<size_t>(4, avail / e->stage_bytes);
+    if (const char* env = getenv("HF_STAGES")) e->nstages = std::max(1, std::min(e->nstages, atoi(env)));
+    if (e->nstages < 1)
       return hf_fail(HF_ERR_STATE, "ensemble tile does not fit in shared memory with this node ordering (halo of " +
                                        std::to_string(e->halo_max) + " rows); use hf_set_ordering(ctx, 2) or a smaller batch");
-    HF_CUDA(cudaStreamSynchronize(c->stream));
+    e->iter_smem = e->stage_bytes * e->nstages;
+    HF_CUDA(cudaStreamSynchronize(c->stream));           // host staging vectors go out of scope
   }
   HF_TRY(e->ctrl.alloc(1, c->stream));
   HF_CUDA(cudaMallocHost(&e->h_ctrl, sizeof(EnsCtrl)));
   DevBuf<int> bad;
   HF_TRY(bad.alloc(1, c->stream));
   ENS_DISPATCH(e->LB, k_ens_diag<LB><<<(unsigned)blocks, HF_ET, 0, c->stream>>>(N, c->rowptr.p, c->col.p, e->base0.p, e->s0.p,
-                                                                                c->bcflag.p, e->ks.p, e->dinv.p, bad.p));
+                                                                                c->bcflag.p, e->ks.p, e->dg.p, bad.p));
   ENS_DISPATCH(e->LB, k_ens_bcast<LB><<<(unsigned)blocks, HF_ET, 0, c->stream>>>(N, c->u.p, e->u.p));
   ENS_DISPATCH(e->LB, k_ens_bcast<LB><<<(unsigned)blocks, HF_ET, 0, c->stream>>>(N, c->gfull.p, e->g.p));
   HF_CUDA(cudaGetLastError());
@@ -576,15 +711,16 @@ static const int kEnsChunk[3] = {8, 32, 128};
 
 static int ens_set_smem(EnsState* e) {
   const int sm = (int)e->iter_smem;
-  if (sm > 48 * 1024) ENS_DISPATCH(e->LB, HF_CUDA(cudaFuncSetAttribute(k_ens_iter<LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)));
+  ENS_DISPATCH(e->LB, HF_CUDA(cudaFuncSetAttribute(k_ens_iter<LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm)));
   return HF_OK;
 }
 
 static void ens_launch_iteration(hf_ctx* c, EnsState* e, int par) {
-  const EnsPatch P{e->R, e->nchunks, e->mcap, e->halo_ptr.p, e->halo_idx.p, e->lcol.p, e->bs.p};
-  ENS_DISPATCH(e->LB, k_ens_iter<LB><<<e->nchunks, HF_ENT, e->iter_smem, c->stream>>>(
-                          c->N, P, par, c->rowptr.p, c->bcflag.p, e->ks.p, e->dinv.p, e->x.p, e->r.p, e->r1.p, e->p0.p, e->p1.p,
-                          e->q.p, e->q1.p, e->part.p, e->ctrl.p));
+  const EnsPatch P{e->nchunks,    e->mcap,         e->halo_cap, e->nstages, (unsigned)e->stage_bytes, e->halo_ptr.p,
+                   e->halo_idx.p, e->rowptr_pad.p, e->lc_off.p, e->lcol.p,  e->bs.p};
+  ENS_DISPATCH(e->LB, k_ens_iter<LB><<<e->igrid, HF_ENT, e->iter_smem, c->stream>>>(P, par, e->ks.p, e->dg.p, e->x.p, e->z.p, e->z1.p,
+                                                                                   e->p0.p, e->p1.p, e->w.p, e->w1.p, e->part.p,
+                                                                                   e->ctrl.p));
 }
 
 static int ens_build_chunks(hf_ctx* c, EnsState* e) {
@@ -664,8 +800,9 @@ extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double 
       c->stat_launches += 1;
     }
     ENS_DISPATCH(e->LB, k_ens_init<LB><<<e->grid, HF_ET, 0, c->stream>>>(N, c->rowptr.p, c->col.p, c->valM.p, e->base0.p, e->s0.p,
-                                                                        c->bcflag.p, e->ks.p, e->g.p, e->u.p, e->dinv.p, e->x.p,
-                                                                        e->r.p, e->part.p, e->ctrl.p, c->rtol));
+                                                                        c->bcflag.p, e->ks.p, e->g.p, e->u.p, e->uprev.p,
+                                                                        e->have_prev ? c->warm : 0.0, e->dg.p, e->x.p, e->z.p,
+                                                                        e->part.p, e->ctrl.p, c->rtol));
     c->stat_launches += 1;
     HF_CUDA(cudaGetLastError());
     int it = 0;
@@ -676,7 +813,9 @@ extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double 
       ENS_DISPATCH(e->LB, k_ens_sample<LB><<<(n + 255) / 256, 256, 0, c->stream>>>(n_watch, n_steps, s, e->watch.p, e->x.p, e->hist.p));
       c->stat_launches += 1;
     }
+    std::swap(e->u.p, e->uprev.p);      // u_{n-1} <- u_n (neither array is an argument of the captured graphs)
     HF_CUDA(cudaMemcpyAsync(e->u.p, e->x.p, sizeof(double) * nb, cudaMemcpyDeviceToDevice, c->stream));
+    e->have_prev = true;
   }
   HF_CUDA(cudaEventRecord(c->ev1, c->stream));
   if (n_watch && n_steps)   // device layout [B, S, W]; only the first nb variants are real
@@ -694,7 +833,8 @@ extern "C" int hf_ens_get_state(hf_ctx* c, double* u) {
   EnsState* e = c->ens;
   const size_t nb = (size_t)c->N * e->B;
   if (e->stage.n < nb) HF_TRY(e->stage.alloc(nb, c->stream));
-  ENS_DISPATCH(e->LB, k_ens_transpose<LB><<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(c->N, c->permuted ? c->rank_d.p : nullptr, e->u.p, e->stage.p));
+  ENS_DISPATCH(e->LB, k_ens_transpose<LB><<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(c->N, c->permuted ? c->rank_d.p : nullptr,
+                                                                                            e->u.p, e->stage.p));
   HF_CUDA(cudaGetLastError());
   return e->stage.download(u, (size_t)c->N * e->nb, c->stream);
 }

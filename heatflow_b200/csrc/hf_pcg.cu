@@ -157,28 +157,39 @@ k_pcg_iter(PatchView A, int par, IterStage S, double* __restrict__ x, double* __
     s_ctl_d[1] = *(volatile double*)&c->beta;
     if (d == 0) {
       for (int st = 0; st < S.nstages; ++st) hf_mbar_init(&full[st], 1);
-      for (int j = 0; j < min(S.nstages, nloc); ++j) {
-        const int ch = blockIdx.x + j * G;
-        hf_issue_chunk<R>(A, ch, A.slice_ptr[ch * SPC], A.slice_ptr[(ch + 1) * SPC], smraw + (size_t)j * S.stage_bytes, S.mat_cap,
-                          S.halo_cap, x, ro, po, qo, &full[j]);
+      int e0[4], e1[4];                 // all extents first: one round trip instead of one per stage
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = min((int)blockIdx.x + j * G, A.nchunks - 1);
+        e0[j] = A.slice_ptr[ch * SPC];
+        e1[j] = A.slice_ptr[(ch + 1) * SPC];
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < min(S.nstages, nloc))
+          hf_issue_chunk<R>(A, blockIdx.x + j * G, e0[j], e1[j], smraw + (size_t)j * S.stage_bytes, S.mat_cap, S.halo_cap, x, ro,
+                            po, qo, &full[j]);
     }
   }
   // ---- halo pipeline prologue: extents of chunks 0..2, indices of chunks 0..1, values of chunk 0
-  int hp_a = 0, nh_a = 0, hp_b = 0, nh_b = 0, hp_c = 0, nh_c = 0;
+  // (list begin, list end) per chunk; the subtraction happens where the count is used, one iteration after
+  // the loads were issued, so that no load latency is exposed inside the chunk loop
+  int hp_a = 0, he_a = 0, hp_b = 0, he_b = 0, hp_c = 0, he_c = 0;
   if (nloc > 0) {
     hp_a = A.halo_ptr[blockIdx.x];
-    nh_a = A.halo_ptr[blockIdx.x + 1] - hp_a;
+    he_a = A.halo_ptr[blockIdx.x + 1];
   }
   if (nloc > 1) {
     hp_b = A.halo_ptr[blockIdx.x + G];
-    nh_b = A.halo_ptr[blockIdx.x + G + 1] - hp_b;
+    he_b = A.halo_ptr[blockIdx.x + G + 1];
   }
   if (nloc > 2) {
     hp_c = A.halo_ptr[blockIdx.x + 2 * G];
-    nh_c = A.halo_ptr[blockIdx.x + 2 * G + 1] - hp_c;
+    he_c = A.halo_ptr[blockIdx.x + 2 * G + 1];
   }
-  int g_b = (tid < nh_b) ? A.halo_idx[hp_b + tid] : -1;
+  const int nh_b0 = he_b - hp_b;
+  int nh_a = he_a - hp_a;
+  int g_b = (tid < nh_b0) ? A.halo_idx[hp_b + tid] : -1;
   double hr = 0.0, hp = 0.0, hq = 0.0;
   if (tid < nh_a) {
     const int g = A.halo_idx[hp_a + tid];
@@ -242,15 +253,15 @@ k_pcg_iter(PatchView A, int par, IterStage S, double* __restrict__ x, double* __
       hq = qo[g_b];
     }
     hp_a = hp_b;
-    nh_a = nh_b;
-    g_b = (tid < nh_c) ? A.halo_idx[hp_c + tid] : -1;
+    nh_a = he_b - hp_b;
+    g_b = (tid < he_c - hp_c) ? A.halo_idx[hp_c + tid] : -1;
     hp_b = hp_c;
-    nh_b = nh_c;
+    he_b = he_c;
     if (j + 3 < nloc) {
       hp_c = A.halo_ptr[ch + 3 * G];
-      nh_c = A.halo_ptr[ch + 3 * G + 1] - hp_c;
+      he_c = A.halo_ptr[ch + 3 * G + 1];
     } else {
-      nh_c = 0;
+      hp_c = he_c = 0;
     }
     // ---- phase 2: q = Ahat p, everything from shared memory
     if (warp < SPC) {

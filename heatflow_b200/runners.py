@@ -33,6 +33,9 @@ from .solver import HeatSolver
 # already gives ~2e-11 agreement with the sparse-LU path; 1e-14 leaves two orders of margin)
 DEFAULT_RTOL = 1e-14
 DEFAULT_MAX_ITERS = 50000
+# initial guess of every solve: u_n + DEFAULT_WARM * (u_n - u_{n-1}); the stopping test is unchanged, the
+# extrapolated start saves ~15 % of the PCG iterations on the reference configs
+DEFAULT_WARM = 1.0
 
 
 @contextlib.contextmanager
@@ -92,7 +95,7 @@ def prepare_mesh(cfg, stack, mesh_folder, rebuild_mesh):
 
 
 def configure_solver(domain, cell_tags, materials, mat_tag_map, bcs, gaussian_bc, dt, device=0,
-                     rtol=DEFAULT_RTOL, max_iters=DEFAULT_MAX_ITERS, ic_temp=None):
+                     rtol=DEFAULT_RTOL, max_iters=DEFAULT_MAX_ITERS, ic_temp=None, warm=DEFAULT_WARM):
     """HeatSolver with mesh, DG0 tables, Dirichlet sets and the assembled operator."""
     solver = HeatSolver(device)
     nodes = domain.geometry.x[:, :2]
@@ -102,7 +105,7 @@ def configure_solver(domain, cell_tags, materials, mat_tag_map, bcs, gaussian_bc
     dofs, value, gslot, gr = problem.device_bc_arrays(nodes.shape[0], bcs, gaussian_bc, nodes)
     solver.set_bcs(dofs, value, gslot, gr)
     solver.build_operator(dt, axisymmetric=True)
-    solver.set_solver(rtol=rtol, max_iters=max_iters)
+    solver.set_solver(rtol=rtol, max_iters=max_iters, warm=warm)
     if ic_temp is not None:
         solver.set_state(np.full(nodes.shape[0], float(ic_temp)))
     return solver

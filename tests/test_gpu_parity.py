@@ -176,6 +176,20 @@ def test_run_is_bit_reproducible(small_nd, mode):
     assert np.array_equal(out[0][2], out[1][2])
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+def test_warm_start_default_of_the_runners_vs_oracle(mode):
+    # the runners start every solve from u_n + (u_n - u_{n-1}); same 1e-10 bar against the LU oracle
+    c = build_case("geballe_with_diamond", 4.0)
+    s = make_solver(c, warm=1.0, mode=mode)
+    O = make_oracle(c)
+    watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
+    hist, iters, fields = s.run(c.amps, c.ic, c.coeff, watch, keep_fields=True)
+    ohist, ofields = O.run(c.num_steps, watch, keep_fields=True)
+    assert np.abs(hist / ohist - 1).max() <= RTOL_FIELD
+    assert max(np.abs(f / of - 1).max() for f, of in zip(fields, ofields)) <= RTOL_FIELD
+    s.close()
+
+
 def test_warm_start_same_answer(small_wd):
     c = small_wd
     a = make_solver(c, warm=0.0)
