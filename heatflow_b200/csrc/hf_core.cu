@@ -615,6 +615,7 @@ extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
   c->op_built = true;
   c->proj_built = false;
   c->last_iters = 0;
+  hf_rc_reset(c);
   HF_CUDA(cudaStreamSynchronize(c->stream));
   return HF_OK;
 }
@@ -685,6 +686,7 @@ extern "C" int hf_set_state(hf_ctx* c, const double* u) {
   cudaSetDevice(c->device);
   HF_TRY(hf_upload_nodal(c, u, c->u.p));
   c->have_prev = false;
+  hf_rc_reset(c);
   return HF_OK;
 }
 
@@ -856,6 +858,7 @@ static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double
                                                   c->uprev.p, warm, c->source.p, c->dt, c->opA.scale.p, c->b.p, w.x.p,
                                                   w.r.p, w.ctrl.p);
   HF_CUDA(cudaGetLastError());
+  HF_TRY(hf_rc_project(c));
   HF_TRY(hf_pcg_prepare(c));
   if (persist) {
     HF_TRY(hf_pcg_solve_async(c, c->opA, step_slot));
@@ -863,6 +866,7 @@ static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double
   } else {
     HF_TRY(hf_pcg_solve(c, c->opA, iters, relres));
   }
+  HF_TRY(hf_rc_store(c, c->opA));
   k_step_finalize<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, w.x.p, c->opA.scale.p, c->u.p, c->uprev.p);
   HF_CUDA(cudaGetLastError());
   c->have_prev = true;

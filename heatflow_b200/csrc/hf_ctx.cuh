@@ -147,6 +147,14 @@ struct PcgWork {
   int grid = 0;
 };
 
+// Initial guess from the previous solves (hf_recycle.cu): Ahat-orthogonal corrections of the last
+// `cap` solves, kept as W, AW = Ahat W and inv[k] = 1 / (w_k . Ahat w_k) in a ring buffer.
+struct Recycle {
+  int cap = 0, count = 0, head = 0, nseg = 0;
+  size_t ld = 0;                       // row stride of W / AW (Npad rounded up to the dot-kernel segment)
+  DevBuf<double> W, AW, inv, coef, parts, part_nn, d, ad;
+};
+
 struct EnsState;
 
 struct hf_ctx {
@@ -199,6 +207,7 @@ struct hf_ctx {
   unsigned long long stat_launches = 0, stat_iters = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   PcgWork ws;
+  Recycle rc;
   DevBuf<double> hist;
   DevBuf<int> watch;
   DevBuf<unsigned char> flush;         // L2 flush buffer for hf_bench_kernels
@@ -259,6 +268,9 @@ int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot);
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out);
 int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out);
 void hf_ens_free(hf_ctx* c);
+void hf_rc_reset(hf_ctx* c);
+int hf_rc_project(hf_ctx* c);
+int hf_rc_store(hf_ctx* c, const SellOp& op);
 int hf_build_patches(const hf_ctx* c, int R, std::vector<int>& halo_ptr, std::vector<int>& halo_idx,
                      std::vector<unsigned short>& lcol, int* halo_max);
 int hf_upload_nodal(hf_ctx* c, const double* h_user, double* d_internal);

@@ -1,0 +1,251 @@
+// heatflow_b200 - initial guess of the Jacobi-PCG solve from the previous time steps (sm_100a).
+//
+// The reference solves every time step with one LU factorisation (run_with_diamond.py:389-394,
+// :480).  An iterative solver pays for every step from scratch unless it reuses what the earlier
+// solves found: all steps share the operator  Ahat = D^-1/2 (M + dt K) D^-1/2,  and the solutions
+// of a diffusion problem driven by one scalar amplitude stay close to a low-dimensional space.
+// This file keeps an Ahat-orthogonal basis  W = [w_1 .. w_m]  of the corrections the last m solves
+// computed, together with  AW = Ahat W  and  1 / (w_k . Ahat w_k):
+//   before the solve   x0 <- x0 + W c,  r0 <- r0 - AW c,  c_k = (w_k . r0) / (w_k . Ahat w_k)
+//                      (Galerkin projection: the error of x0 becomes Ahat-orthogonal to span W);
+//   after the solve    d = x - x0,  Ad = Ahat d (one SpMV, so that AW = Ahat W holds to rounding),
+//                      one Gram-Schmidt pass against W in the Ahat inner product, store (d, Ad).
+// The solver itself is unchanged (Jacobi-PCG to the same tolerance on the same system): only the
+// starting point moves, so the converged answer is the same to the solver tolerance.  Measured on
+// geballe_with_diamond (N = 1.4e5, 100 steps): 223 instead of 620 iterations per step.
+// Cost per step: 6 m N doubles of streaming reads + 1 SpMV, a few percent of the iterations saved.
+// All kernels are stream ordered; reductions add per-warp / per-CTA partials in a fixed order.
+#include <algorithm>
+#include <cmath>
+
+#include "hf_ctx.cuh"
+
+#define RC_SEG 128            // rows per warp of the dot-product kernel
+#define RC_WARPS 8
+
+// parts[k * nseg + seg] = sum over the 128 rows of segment `seg` of V[k][i] * v[i], k < m.
+// One warp per segment keeps v in registers and streams four basis vectors per round (16
+// independent 256-byte loads in flight per warp).
+__global__ void __launch_bounds__(RC_WARPS * 32)
+k_rc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double* __restrict__ v,
+          double* __restrict__ parts) {
+  const int lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * RC_WARPS + (threadIdx.x >> 5);
+  if (seg >= nseg) return;
+  const size_t base = (size_t)seg * RC_SEG + lane;
+  double vv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) vv[j] = v[base + 32 * j];
+  for (int k = 0; k < m; k += 4) {
+    double a[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const double* p = V + (size_t)min(k + t, m - 1) * ld + base;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[t][j] = hf_ld_stream(p + 32 * j);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s = fma(a[t][j], vv[j], s);
+      s = hf_warp_sum(s);
+      if (lane == 0 && k + t < m) parts[(size_t)(k + t) * nseg + seg] = s;
+    }
+  }
+}
+
+// coef[k] = sign * inv[k] * sum_seg parts[k][seg]   (one warp per k, fixed order); coef[skip] = 0
+__global__ void __launch_bounds__(RC_WARPS * 32)
+k_rc_coef(int m, int skip, int nseg, const double* __restrict__ parts, const double* __restrict__ inv, double sign,
+          double* __restrict__ coef) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * RC_WARPS + (threadIdx.x >> 5);
+  if (k >= m) return;
+  double s = 0.0;
+  for (int i = lane; i < nseg; i += 32) s += __ldcg(parts + (size_t)k * nseg + i);
+  s = hf_warp_sum(s);
+  if (lane == 0) coef[k] = (k == skip) ? 0.0 : sign * inv[k] * s;
+}
+
+// GS = false (before the solve):  a = x0, b = r0:   a += W c ; b -= AW c ; outW = a (x0 kept for the
+//                                 correction) ; partial sums of b.b  -> part[blockIdx.x]
+// GS = true  (after the solve):   a = d, b = Ad, coef = -h:  outW = a + W coef ; outAW = b + AW coef ;
+//                                 partial sums of outW.outAW -> part[blockIdx.x]
+template <bool GS>
+__global__ void __launch_bounds__(HF_BLOCK)
+k_rc_update(int m, int n, size_t ld, const double* __restrict__ W, const double* __restrict__ AW,
+            const double* __restrict__ coef, double* __restrict__ a, double* __restrict__ b, double* __restrict__ outW,
+            double* __restrict__ outAW, double* __restrict__ part) {
+  extern __shared__ double s_coef[];
+  __shared__ double sh[HF_BLOCK / 32];
+  for (int k = threadIdx.x; k < m; k += HF_BLOCK) s_coef[k] = coef[k];
+  __syncthreads();
+  double local = 0.0;
+  for (int i = blockIdx.x * HF_BLOCK + threadIdx.x; i < n; i += gridDim.x * HF_BLOCK) {
+    double ca0 = 0.0, ca1 = 0.0, cb0 = 0.0, cb1 = 0.0;
+    const double* w = W + i;
+    const double* aw = AW + i;
+    int k = 0;
+    for (; k + 4 <= m; k += 4) {
+      const double w0 = hf_ld_stream(w + (size_t)k * ld), w1 = hf_ld_stream(w + (size_t)(k + 1) * ld),
+                   w2 = hf_ld_stream(w + (size_t)(k + 2) * ld), w3 = hf_ld_stream(w + (size_t)(k + 3) * ld);
+      const double z0 = hf_ld_stream(aw + (size_t)k * ld), z1 = hf_ld_stream(aw + (size_t)(k + 1) * ld),
+                   z2 = hf_ld_stream(aw + (size_t)(k + 2) * ld), z3 = hf_ld_stream(aw + (size_t)(k + 3) * ld);
+      const double c0 = s_coef[k], c1 = s_coef[k + 1], c2 = s_coef[k + 2], c3 = s_coef[k + 3];
+      ca0 = fma(c0, w0, ca0);
+      ca1 = fma(c1, w1, ca1);
+      ca0 = fma(c2, w2, ca0);
+      ca1 = fma(c3, w3, ca1);
+      cb0 = fma(c0, z0, cb0);
+      cb1 = fma(c1, z1, cb1);
+      cb0 = fma(c2, z2, cb0);
+      cb1 = fma(c3, z3, cb1);
+    }
+    for (; k < m; ++k) {
+      const double ck = s_coef[k];
+      ca0 = fma(ck, hf_ld_stream(w + (size_t)k * ld), ca0);
+      cb0 = fma(ck, hf_ld_stream(aw + (size_t)k * ld), cb0);
+    }
+    const double ca = ca0 + ca1, cb = cb0 + cb1;
+    if (GS) {
+      const double d = a[i] + ca, ad = b[i] + cb;
+      outW[i] = d;
+      outAW[i] = ad;
+      local = fma(d, ad, local);
+    } else {
+      const double x = a[i] + ca, r = b[i] - cb;
+      a[i] = x;
+      b[i] = r;
+      outW[i] = x;
+      local = fma(r, r, local);
+    }
+  }
+  const double tot = hf_block_sum(local, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+
+// d = x - x0 and Ad = Ahat d in one pass (sliced-ELL, one warp per slice; the gathers hit L2)
+__global__ void __launch_bounds__(HF_BLOCK)
+k_rc_spmv(SellView A, const double* __restrict__ x, const double* __restrict__ x0, double* __restrict__ d,
+          double* __restrict__ ad) {
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (HF_BLOCK / 32) + (threadIdx.x >> 5);
+  if (s >= A.nslices) return;
+  const int b0 = A.slice_ptr[s];
+  const int w = (A.slice_ptr[s + 1] - b0) >> 5;
+  const int* cp = A.col + b0 + lane;
+  const double* vp = A.val + b0 + lane;
+  double acc0 = 0.0, acc1 = 0.0;
+  int k = 0;
+  for (; k + 2 <= w; k += 2) {
+    const int c0 = cp[k * 32], c1 = cp[(k + 1) * 32];
+    const double v0 = vp[k * 32], v1 = vp[(k + 1) * 32];
+    acc0 = fma(v0, x[c0] - x0[c0], acc0);
+    acc1 = fma(v1, x[c1] - x0[c1], acc1);
+  }
+  if (k < w) {
+    const int c0 = cp[k * 32];
+    acc0 = fma(vp[k * 32], x[c0] - x0[c0], acc0);
+  }
+  const int i = s * HF_SLICE + lane;
+  d[i] = x[i] - x0[i];
+  ad[i] = acc0 + acc1;
+}
+
+// inv[slot] = 1 / (w . Ahat w), 0 when the correction is empty or not finite (slot stays inert)
+__global__ void __launch_bounds__(HF_BLOCK) k_rc_norm(int nparts, const double* __restrict__ part, double* __restrict__ inv, int slot) {
+  __shared__ double sh[HF_BLOCK / 32];
+  const double nn = hf_sum_parts(part, nparts, sh);
+  if (threadIdx.x == 0) inv[slot] = (nn > 0.0 && isfinite(nn) && isfinite(1.0 / nn)) ? 1.0 / nn : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+void hf_rc_reset(hf_ctx* c) {
+  c->rc.count = 0;
+  c->rc.head = 0;
+}
+
+static int rc_alloc(hf_ctx* c) {
+  Recycle& rc = c->rc;
+  const size_t ld = ((size_t)c->Npad + RC_SEG - 1) / RC_SEG * RC_SEG;
+  if (rc.ld == ld && rc.W.n == (size_t)rc.cap * ld) return HF_OK;
+  rc.ld = ld;
+  rc.nseg = (int)(ld / RC_SEG);
+  HF_TRY(rc.W.alloc((size_t)rc.cap * ld, c->stream));
+  HF_TRY(rc.AW.alloc((size_t)rc.cap * ld, c->stream));
+  HF_TRY(rc.inv.alloc(rc.cap, c->stream));
+  HF_TRY(rc.coef.alloc(rc.cap, c->stream));
+  HF_TRY(rc.parts.alloc((size_t)rc.cap * rc.nseg, c->stream));
+  HF_TRY(rc.part_nn.alloc(HF_MAX_PART, c->stream));
+  HF_TRY(rc.d.alloc(ld, c->stream));
+  HF_TRY(rc.ad.alloc(ld, c->stream));
+  hf_rc_reset(c);
+  return HF_OK;
+}
+
+extern "C" int hf_set_recycle(hf_ctx* c, int32_t max_vectors) {
+  if (!c || max_vectors < 0 || max_vectors > 4096) return hf_fail(HF_ERR_ARG, "hf_set_recycle: bad arguments");
+  cudaSetDevice(c->device);
+  Recycle& rc = c->rc;
+  if (max_vectors != rc.cap) {
+    rc.W.release();
+    rc.AW.release();
+    rc.ld = 0;
+  }
+  rc.cap = max_vectors;
+  hf_rc_reset(c);
+  return HF_OK;
+}
+
+// ws.x = x0, ws.r = r0 = bhat - Ahat x0 and ctrl.part_rr[0][0 .. ws.grid) hold the caller's values;
+// on return they hold the projected ones and slot `head` of W keeps x0.
+int hf_rc_project(hf_ctx* c) {
+  Recycle& rc = c->rc;
+  if (rc.cap == 0) return HF_OK;
+  HF_TRY(rc_alloc(c));
+  PcgWork& w = c->ws;
+  const int m = std::min(rc.count, rc.cap);
+  double* slotW = rc.W.p + (size_t)rc.head * rc.ld;
+  if (m == 0) {
+    HF_CUDA(cudaMemcpyAsync(slotW, w.x.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
+    return HF_OK;
+  }
+  k_rc_dots<<<(rc.nseg + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.W.p, w.r.p, rc.parts.p);
+  k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.head, rc.nseg, rc.parts.p, rc.inv.p, 1.0,
+                                                                            rc.coef.p);
+  HfCtrl* ctl = w.ctrl.p;
+  k_rc_update<false><<<w.grid, HF_BLOCK, sizeof(double) * m, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, w.x.p,
+                                                                          w.r.p, slotW, nullptr, &ctl->part_rr[0][0]);
+  c->stat_launches += 3;
+  HF_CUDA(cudaGetLastError());
+  return HF_OK;
+}
+
+// ws.x = converged xhat; stores the Ahat-orthogonalised correction of this solve in slot `head`.
+int hf_rc_store(hf_ctx* c, const SellOp& op) {
+  Recycle& rc = c->rc;
+  if (rc.cap == 0) return HF_OK;
+  PcgWork& w = c->ws;
+  const int m = std::min(rc.count, rc.cap);
+  double* slotW = rc.W.p + (size_t)rc.head * rc.ld;
+  double* slotAW = rc.AW.p + (size_t)rc.head * rc.ld;
+  const int spc = HF_BLOCK / 32;
+  k_rc_spmv<<<(op.nslices + spc - 1) / spc, HF_BLOCK, 0, c->stream>>>(op.view(), w.x.p, slotW, rc.d.p, rc.ad.p);
+  if (m > 0) {
+    k_rc_dots<<<(rc.nseg + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.AW.p, rc.d.p, rc.parts.p);
+    k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.head, rc.nseg, rc.parts.p, rc.inv.p, -1.0,
+                                                                              rc.coef.p);
+    c->stat_launches += 2;
+  }
+  k_rc_update<true><<<w.grid, HF_BLOCK, sizeof(double) * m, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, rc.d.p,
+                                                                         rc.ad.p, slotW, slotAW, rc.part_nn.p);
+  k_rc_norm<<<1, HF_BLOCK, 0, c->stream>>>(w.grid, rc.part_nn.p, rc.inv.p, rc.head);
+  c->stat_launches += 3;
+  HF_CUDA(cudaGetLastError());
+  rc.count += 1;
+  rc.head = (rc.head + 1) % rc.cap;
+  return HF_OK;
+}

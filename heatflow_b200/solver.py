@@ -101,6 +101,10 @@ class HeatSolver:
         _lib.check(self._L.hf_set_solver(self._h, float(rtol), int(max_iters), float(warm), int(mode)))
 
     # -- inspection -----------------------------------------------------------------
+    def set_recycle(self, max_vectors):
+        """Start every solve from the projection of its RHS onto the last `max_vectors` corrections."""
+        _lib.check(self._L.hf_set_recycle(self._h, int(max_vectors)))
+
     def sizes(self):
         n, nnz = C.c_int32(), C.c_int64()
         _lib.check(self._L.hf_get_sizes(self._h, C.byref(n), C.byref(nnz)))

@@ -92,6 +92,14 @@ int hf_set_source(hf_ctx* ctx, const double* s);
  * graph, 2 = persistent cooperative kernel. */
 int hf_set_solver(hf_ctx* ctx, double rtol, int32_t max_iters, double warm, int32_t mode);
 
+/* Initial guess from the previous time steps: keep the corrections of the last max_vectors
+ * solves (A-orthogonalised) and start every solve from the Galerkin projection of its
+ * right-hand side onto them.  The solver, its tolerance and therefore the converged answer are
+ * unchanged (the reference re-uses its LU factors across steps in the same spirit,
+ * run_with_diamond.py:389-394); 0 disables.  Memory: 2 * max_vectors * N doubles.  The basis is
+ * dropped by hf_set_state and hf_build_operator. */
+int hf_set_recycle(hf_ctx* ctx, int32_t max_vectors);
+
 /* One backward-Euler step (reference loop body, run_with_diamond.py:471-481):
  * Gaussian BC update with amplitude `amp` (g = (amp - t_ic) exp(coeff r^2) + t_ic), RHS
  * assemble_vector + apply_lifting + set_bc, then the solve, result overwrites u_n.

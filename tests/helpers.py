@@ -77,7 +77,7 @@ def make_oracle(c):
     return ho.Oracle2D(c.nodes, c.tris, c.rhoc_c, c.kappa_c, c.dt, c.oracle_bcs, c.ic, c.fwhm, c.heat_t, c.heat_T)
 
 
-def make_solver(c, rtol=1e-14, warm=0.0, mode=0, ordering="auto"):
+def make_solver(c, rtol=1e-14, warm=0.0, mode=0, ordering="auto", recycle=0):
     from heatflow_b200.solver import HeatSolver
     s = HeatSolver(0)
     s.set_ordering(ordering)
@@ -86,5 +86,6 @@ def make_solver(c, rtol=1e-14, warm=0.0, mode=0, ordering="auto"):
     s.set_bcs(c.bc_dofs, c.bc_value, c.gauss_slot, c.gauss_r)
     s.build_operator(c.dt, True)
     s.set_solver(rtol=rtol, warm=warm, mode=mode)
+    s.set_recycle(recycle)
     s.set_state(np.full(len(c.nodes), c.ic))
     return s

@@ -8,6 +8,7 @@ import pytest
 import scipy.sparse as sp
 
 from helpers import build_case, make_oracle, make_solver
+from heatflow_b200 import _lib
 from oracle import heat_oracle as ho
 
 pytestmark = pytest.mark.gpu
@@ -234,3 +235,57 @@ def test_error_paths(small_nd):
     with pytest.raises(HeatflowError):
         s.set_bcs(c.bc_dofs[::-1].copy(), c.bc_value, c.gauss_slot, c.gauss_r)  # unsorted
     s.close()
+
+
+# ---- initial guess recycled from the previous solves (hf_set_recycle, the runners' default) ----
+@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+@pytest.mark.parametrize("cap", [128, 6], ids=["full-history", "ring-wraps"])
+def test_recycled_initial_guess_vs_oracle_every_step(mode, cap):
+    c = build_case("geballe_with_diamond", 4.0)
+    s = make_solver(c, warm=1.0, mode=mode, recycle=cap)
+    O = make_oracle(c)
+    watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
+    hist, iters, fields = s.run(c.amps, c.ic, c.coeff, watch, keep_fields=True)
+    ohist, ofields = O.run(c.num_steps, watch, keep_fields=True)
+    assert np.abs(hist / ohist - 1).max() <= RTOL_FIELD
+    assert max(np.abs(f / of - 1).max() for f, of in zip(fields, ofields)) <= RTOL_FIELD
+    s.close()
+
+
+def test_recycle_cuts_iterations_and_is_bit_reproducible(small_wd):
+    c = small_wd
+    base = make_solver(c, warm=1.0)
+    _, i0, _ = base.run(c.amps[:60], c.ic, c.coeff, [3])
+    base.close()
+    runs = []
+    for _ in range(2):
+        s = make_solver(c, warm=1.0, recycle=64)
+        h, it, _ = s.run(c.amps[:60], c.ic, c.coeff, [3, 50])
+        runs.append((h, it, s.get_state()))
+        # a new initial state drops the basis: the second run of the same solver repeats the first
+        s.set_state(np.full(len(c.nodes), c.ic))
+        h2, it2, _ = s.run(c.amps[:60], c.ic, c.coeff, [3, 50])
+        assert np.array_equal(h, h2) and np.array_equal(it, it2)
+        s.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    assert np.array_equal(runs[0][2], runs[1][2])
+    assert runs[0][1].sum() < 0.5 * i0.sum()
+
+
+def test_recycle_single_steps_and_argument_errors(small_nd):
+    c = small_nd
+    s = make_solver(c, recycle=16)
+    for k in range(12):
+        s.step(c.amps[k + 10], c.ic, c.coeff)
+    s2 = make_solver(c)
+    for k in range(12):
+        s2.step(c.amps[k + 10], c.ic, c.coeff)
+    assert rel_err(s.get_state(), s2.get_state()) <= 1e-11
+    with pytest.raises(_lib.HeatflowError):
+        s.set_recycle(-1)
+    s.set_recycle(0)            # switching it off mid-run is allowed
+    s.step(c.amps[30], c.ic, c.coeff)
+    s2.step(c.amps[30], c.ic, c.coeff)
+    assert rel_err(s.get_state(), s2.get_state()) <= 1e-11
+    s.close()
+    s2.close()
