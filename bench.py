@@ -20,7 +20,7 @@ Extra objects on the JSON line:
   roofline_1m   ``k_pcg_iter`` (streaming kernel, one launch per PCG iteration) on the >= 1 M-dof
                 refinement of ``cfgs/konopkova.yaml`` (BASELINE config #4), timed inside a real solve:
                 CUDA events around the step loop / launches, so launch gaps count against it.
-  sweep         ensemble tile of 16 (k, fwhm) variants per GPU through ``hf_ens_*`` -> sims/s.
+  sweep         tile of 16 (k, fwhm) variants per GPU through the sweep engine's path -> sims/s.
   cpu_baseline  the scipy sparse-LU oracle on this host (1 core), bounded sample.
 """
 import argparse
@@ -240,25 +240,48 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     barrier()
 
-    # ---- sweep tile: 16 (k, fwhm) variants of config #5 per GPU through the ensemble kernels
-    sweep_ms = 0.0
+    # ---- sweep tile: 16 (k, fwhm) variants of config #5 per GPU through the sweep engine's path for this mesh
+    # (heatflow_b200/sweep.py: 'serial' when the mesh fits on chip, else the batched ensemble kernels);
+    # wall clock between device synchronisations, operator re-assembly per conductivity included
+    sweep_ms, sweep_engine = 0.0, None
     if not args.skip_sweep:
         from heatflow_b200 import problem as _problem
         B = 16
-        ks = np.logspace(0.0, 2.0, 64)[(np.arange(B) + 16 * rank) % 64]
+        kgrid = np.logspace(0.0, 2.0, 64)
+        ks = np.repeat(kgrid[[(5 + 16 * rank) % 64, (37 + 16 * rank) % 64]], B // 2)     # two conductivities x 8 widths
         fw = np.logspace(-6.0, -4.0, 64)[(np.arange(B) * 5 + rank) % 64]
-        se = configured_solver(c, local_rank, args.rtol, ordering="hilbert")
-        sample_tag = int(c.tags[[m.name for m in c.mats].index("p_sample")])
         coeffs = [_problem.gaussian_coeff(f) for f in fw]
-        se.set_state(u0)
-        se.ens_create(ks, coeffs, sample_tag)
-        se.ens_run(c.amps[20:22], c.ic, watch)                  # warm-up
-        se.ens_destroy()
-        se.set_state(u0)
-        se.ens_create(ks, coeffs, sample_tag)
+        i_sample = [m.name for m in c.mats].index("p_sample")
+        sweep_engine = "serial" if s.on_chip() else "ensemble"
+        if sweep_engine == "serial":
+            se = configured_solver(c, local_rank, args.rtol, warm=args.warm_start, recycle=args.recycle)
+
+            def sweep_pass(n_steps):
+                k_now = None
+                for kv, cf in zip(ks, coeffs):
+                    if k_now != kv:
+                        kap = c.kappa_t.copy()
+                        kap[i_sample] = kv
+                        se.set_materials(c.tags, kap, c.rhoc_t)
+                        se.build_operator(c.dt, True)
+                        k_now = kv
+                    se.set_state(u0)
+                    se.run(c.amps[:n_steps], c.ic, cf, watch)
+        else:
+            se = configured_solver(c, local_rank, args.rtol, warm=args.warm_start, ordering="hilbert")
+            sample_tag = int(c.tags[i_sample])
+
+            def sweep_pass(n_steps):
+                se.set_state(u0)
+                se.ens_create(ks, coeffs, sample_tag)
+                se.ens_run(c.amps[:n_steps], c.ic, watch)
+                se.ens_destroy()
+        sweep_pass(min(steps, 8))                                  # warm-up
         barrier()
-        se.ens_run(c.amps[:steps], c.ic, watch)
-        sweep_ms = se.stats()["run_ms"]
+        t0 = time.perf_counter()
+        sweep_pass(steps)
+        torch.cuda.synchronize()
+        sweep_ms = (time.perf_counter() - t0) * 1e3
         barrier()
         se.close()
 
@@ -316,10 +339,11 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roof,
     }
     if sweep_ms > 0.0:
-        line["sweep"] = {"sims_per_s": world * 16 / (sweep_ms * 1e-3), "variants": world * 16, "batch_per_gpu": 16, "steps": steps,
-                         "dof_timesteps_per_s": world * 16 * n * steps / (sweep_ms * 1e-3),
-                         "note": "one ensemble tile per GPU, device-timed (max over ranks); the 4096-variant sweep of "
-                                 "config #5 is 256 such tiles"}
+        line["sweep"] = {"sims_per_s": world * 16 / (sweep_ms * 1e-3), "variants": world * 16, "variants_per_gpu": 16, "steps": steps,
+                         "engine": sweep_engine, "dof_timesteps_per_s": world * 16 * n * steps / (sweep_ms * 1e-3),
+                         "note": "one tile of 16 variants (2 conductivities x 8 widths) per GPU through the sweep engine, wall "
+                                 "clock incl. operator re-assembly (max over ranks); the 4096-variant sweep of config #5 is "
+                                 "256 such tiles"}
     # >= 1 M-dof mesh (north_star target for the SpMV roofline): BASELINE config #4, konopkova cfg refined x 0.35
     if not args.skip_large:
         from helpers import build_case

@@ -941,6 +941,14 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
   return HF_OK;
 }
 
+extern "C" int hf_get_solver_path(hf_ctx* c) {
+  if (!c) return hf_fail(HF_ERR_ARG, "null context");
+  if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_get_solver_path: operator not built");
+  bool persist = false;
+  HF_TRY(pick_persist(c, c->opA, &persist));
+  return persist ? 2 : 1;
+}
+
 extern "C" int hf_get_stats(hf_ctx* c, double* st) {
   if (!c || !st) return hf_fail(HF_ERR_ARG, "hf_get_stats: null argument");
   st[0] = c->stat_run_ms;

@@ -147,10 +147,10 @@ struct PcgWork {
   int grid = 0;
 };
 
-// Initial guess from the previous solves (hf_recycle.cu): Ahat-orthogonal corrections of the last
-// `cap` solves, kept as W, AW = Ahat W and inv[k] = 1 / (w_k . Ahat w_k) in a ring buffer.
+// Initial guess from the previous solves (hf_recycle.cu): Ahat-orthogonal corrections of up to `cap`
+// solves, kept as W, AW = Ahat W and inv[k] = 1 / (w_k . Ahat w_k); frozen once full.
 struct Recycle {
-  int cap = 0, count = 0, head = 0, nseg = 0;
+  int cap = 0, count = 0, nseg = 0;
   size_t ld = 0;                       // row stride of W / AW (Npad rounded up to the dot-kernel segment)
   DevBuf<double> W, AW, inv, coef, parts, part_nn, d, ad;
 };

@@ -4,7 +4,7 @@
 // :480).  An iterative solver pays for every step from scratch unless it reuses what the earlier
 // solves found: all steps share the operator  Ahat = D^-1/2 (M + dt K) D^-1/2,  and the solutions
 // of a diffusion problem driven by one scalar amplitude stay close to a low-dimensional space.
-// This file keeps an Ahat-orthogonal basis  W = [w_1 .. w_m]  of the corrections the last m solves
+// This file keeps an Ahat-orthogonal basis  W = [w_1 .. w_m]  of the corrections the first m solves
 // computed, together with  AW = Ahat W  and  1 / (w_k . Ahat w_k):
 //   before the solve   x0 <- x0 + W c,  r0 <- r0 - AW c,  c_k = (w_k . r0) / (w_k . Ahat w_k)
 //                      (Galerkin projection: the error of x0 becomes Ahat-orthogonal to span W);
@@ -55,9 +55,9 @@ k_rc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double
   }
 }
 
-// coef[k] = sign * inv[k] * sum_seg parts[k][seg]   (one warp per k, fixed order); coef[skip] = 0
+// coef[k] = sign * inv[k] * sum_seg parts[k][seg]   (one warp per k, fixed order)
 __global__ void __launch_bounds__(RC_WARPS * 32)
-k_rc_coef(int m, int skip, int nseg, const double* __restrict__ parts, const double* __restrict__ inv, double sign,
+k_rc_coef(int m, int nseg, const double* __restrict__ parts, const double* __restrict__ inv, double sign,
           double* __restrict__ coef) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * RC_WARPS + (threadIdx.x >> 5);
@@ -65,11 +65,11 @@ k_rc_coef(int m, int skip, int nseg, const double* __restrict__ parts, const dou
   double s = 0.0;
   for (int i = lane; i < nseg; i += 32) s += __ldcg(parts + (size_t)k * nseg + i);
   s = hf_warp_sum(s);
-  if (lane == 0) coef[k] = (k == skip) ? 0.0 : sign * inv[k] * s;
+  if (lane == 0) coef[k] = sign * inv[k] * s;
 }
 
 // GS = false (before the solve):  a = x0, b = r0:   a += W c ; b -= AW c ; outW = a (x0 kept for the
-//                                 correction) ; partial sums of b.b  -> part[blockIdx.x]
+//                                 correction; null once the basis is frozen) ; partial sums of b.b  -> part[blockIdx.x]
 // GS = true  (after the solve):   a = d, b = Ad, coef = -h:  outW = a + W coef ; outAW = b + AW coef ;
 //                                 partial sums of outW.outAW -> part[blockIdx.x]
 template <bool GS>
@@ -117,7 +117,7 @@ k_rc_update(int m, int n, size_t ld, const double* __restrict__ W, const double*
       const double x = a[i] + ca, r = b[i] - cb;
       a[i] = x;
       b[i] = r;
-      outW[i] = x;
+      if (outW) outW[i] = x;
       local = fma(r, r, local);
     }
   }
@@ -163,10 +163,7 @@ __global__ void __launch_bounds__(HF_BLOCK) k_rc_norm(int nparts, const double* 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-void hf_rc_reset(hf_ctx* c) {
-  c->rc.count = 0;
-  c->rc.head = 0;
-}
+void hf_rc_reset(hf_ctx* c) { c->rc.count = 0; }
 
 static int rc_alloc(hf_ctx* c) {
   Recycle& rc = c->rc;
@@ -201,21 +198,24 @@ extern "C" int hf_set_recycle(hf_ctx* c, int32_t max_vectors) {
 }
 
 // ws.x = x0, ws.r = r0 = bhat - Ahat x0 and ctrl.part_rr[0][0 .. ws.grid) hold the caller's values;
-// on return they hold the projected ones and slot `head` of W keeps x0.
+// on return they hold the projected ones and the next free slot of W keeps x0.
+// Once `cap` corrections are stored the basis is frozen: every vector is Ahat-orthogonal to the others
+// and carries a direction the later solutions keep using (the low-order Krylov vectors of the time
+// stepping), so evicting the oldest one costs a full-length solve per step (measured); the late
+// corrections are the small ones and are simply not recorded any more.
 int hf_rc_project(hf_ctx* c) {
   Recycle& rc = c->rc;
   if (rc.cap == 0) return HF_OK;
   HF_TRY(rc_alloc(c));
   PcgWork& w = c->ws;
   const int m = std::min(rc.count, rc.cap);
-  double* slotW = rc.W.p + (size_t)rc.head * rc.ld;
+  double* slotW = (m < rc.cap) ? rc.W.p + (size_t)m * rc.ld : nullptr;
   if (m == 0) {
     HF_CUDA(cudaMemcpyAsync(slotW, w.x.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
     return HF_OK;
   }
   k_rc_dots<<<(rc.nseg + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.W.p, w.r.p, rc.parts.p);
-  k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.head, rc.nseg, rc.parts.p, rc.inv.p, 1.0,
-                                                                            rc.coef.p);
+  k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.parts.p, rc.inv.p, 1.0, rc.coef.p);
   HfCtrl* ctl = w.ctrl.p;
   k_rc_update<false><<<w.grid, HF_BLOCK, sizeof(double) * m, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, w.x.p,
                                                                           w.r.p, slotW, nullptr, &ctl->part_rr[0][0]);
@@ -224,28 +224,26 @@ int hf_rc_project(hf_ctx* c) {
   return HF_OK;
 }
 
-// ws.x = converged xhat; stores the Ahat-orthogonalised correction of this solve in slot `head`.
+// ws.x = converged xhat; stores the Ahat-orthogonalised correction of this solve in the next free slot.
 int hf_rc_store(hf_ctx* c, const SellOp& op) {
   Recycle& rc = c->rc;
-  if (rc.cap == 0) return HF_OK;
+  if (rc.cap == 0 || rc.count >= rc.cap) return HF_OK;
   PcgWork& w = c->ws;
-  const int m = std::min(rc.count, rc.cap);
-  double* slotW = rc.W.p + (size_t)rc.head * rc.ld;
-  double* slotAW = rc.AW.p + (size_t)rc.head * rc.ld;
+  const int m = rc.count;
+  double* slotW = rc.W.p + (size_t)m * rc.ld;
+  double* slotAW = rc.AW.p + (size_t)m * rc.ld;
   const int spc = HF_BLOCK / 32;
   k_rc_spmv<<<(op.nslices + spc - 1) / spc, HF_BLOCK, 0, c->stream>>>(op.view(), w.x.p, slotW, rc.d.p, rc.ad.p);
   if (m > 0) {
     k_rc_dots<<<(rc.nseg + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.AW.p, rc.d.p, rc.parts.p);
-    k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.head, rc.nseg, rc.parts.p, rc.inv.p, -1.0,
-                                                                              rc.coef.p);
+    k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.parts.p, rc.inv.p, -1.0, rc.coef.p);
     c->stat_launches += 2;
   }
   k_rc_update<true><<<w.grid, HF_BLOCK, sizeof(double) * m, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, rc.d.p,
                                                                          rc.ad.p, slotW, slotAW, rc.part_nn.p);
-  k_rc_norm<<<1, HF_BLOCK, 0, c->stream>>>(w.grid, rc.part_nn.p, rc.inv.p, rc.head);
+  k_rc_norm<<<1, HF_BLOCK, 0, c->stream>>>(w.grid, rc.part_nn.p, rc.inv.p, m);
   c->stat_launches += 3;
   HF_CUDA(cudaGetLastError());
   rc.count += 1;
-  rc.head = (rc.head + 1) % rc.cap;
   return HF_OK;
 }

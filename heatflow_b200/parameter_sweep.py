@@ -9,10 +9,12 @@ cfg editing, :290-540 driver, :543-604 CLI).  What differs is how the runs execu
   ---------------------------------------------  ---------------------------------------------
   one spawned CPU process per parameter set,     variants of a width group (same mesh) advance in
   each re-reading the mesh, re-assembling and    tiles of ``batch`` simulations through the batched
-  LU-factorising (``mp.Pool``)                   multi-RHS CUDA kernels; tiles are sharded over the
-                                                 GPUs (torchrun ranks, or ``num_processes`` spawned
-                                                 GPU workers) with one final gather of the watcher
-                                                 histories (``mode='ensemble'``, the default)
+  LU-factorising (``mp.Pool``)                   multi-RHS CUDA kernels (``mode='ensemble'``) or, when
+                                                 the mesh fits on chip, one after the other on the
+                                                 resident mesh (``mode='serial'``; ``'auto'``, the
+                                                 default, picks); tiles are sharded over the GPUs
+                                                 (torchrun ranks, or ``num_processes`` spawned GPU
+                                                 workers) with one final gather of the watcher histories
   ---------------------------------------------  ---------------------------------------------
   ``mode='per_run'`` (forced by ``write_xdmf=True``) keeps the reference's behaviour of calling
   ``run_simulation`` once per parameter set, which also writes the XDMF and gradient CSV files.
@@ -145,7 +147,7 @@ def get_mesh_folder_for_width(base_mesh_folder, width):
 # ----------------------------------------------------------------------------------------
 # ensemble execution of one width group
 # ----------------------------------------------------------------------------------------
-def _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print):
+def _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine="auto"):
     """Set the group's mesh up on ``device`` and run this rank's tiles.
     Returns (idx, hist, iters, secs, errors, step_times)."""
     cfg0 = modify_config_for_parameters(base_config, combinations[0]['fwhm'], combinations[0]['k'], combinations[0]['width'])
@@ -156,7 +158,7 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
         watch = sim.watcher_nodes(list(get_watcher_points(cfg0).values()))
         fwhm = np.array([c['fwhm'] for c in combinations])
         k = np.array([c['k'] for c in combinations])
-        out = sweep.run_tiles(sim, fwhm, k, tiles, watch)
+        out = sweep.run_tiles(sim, fwhm, k, tiles, watch, engine=engine)
         return out + (sim.step_t.copy(),)
     finally:
         sim.close()
@@ -165,8 +167,8 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
 def _device_worker(args):
     """Spawned GPU worker (one per device) for sweeps launched without torchrun."""
     set_single_thread()
-    base_config, combinations, mesh_folder, batch, device, tiles, suppress_print = args
-    return _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print)
+    base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine = args
+    return _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine)
 
 
 def _write_run_outputs(output_dir, base_config, combo, step_t, hist, names):
@@ -189,16 +191,18 @@ def _visible_gpus():
 
 def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width_range, num_points,
                         base_mesh_folder="meshes", write_xdmf=False, suppress_print=True, num_processes=None,
-                        mode="ensemble", batch=16):
+                        mode="auto", batch=16):
     """Run the sweep (parameter_sweep.py:290-540).  Returns ``(results, failed_runs)`` on rank 0
     (``([], [])`` on the other torchrun ranks).
 
     ``num_processes``: GPU worker processes when not launched under torchrun (default: every
-    visible GPU).  ``mode``: 'ensemble' (batched kernels, ``batch`` variants per tile) or 'per_run'.
+    visible GPU).  ``mode``: 'ensemble' (batched kernels, ``batch`` variants per tile), 'serial' (one
+    simulation after the other on the resident mesh), 'auto' (serial when the mesh fits on chip, else
+    ensemble) or 'per_run' (one ``run_simulation`` call per parameter set, as the reference).
     """
     set_single_thread()
-    if mode not in ("ensemble", "per_run"):
-        raise ValueError("mode must be 'ensemble' or 'per_run'")
+    if mode not in ("auto", "ensemble", "serial", "per_run"):
+        raise ValueError("mode must be 'auto', 'ensemble', 'serial' or 'per_run'")
     if write_xdmf:
         mode = "per_run"                       # field output needs every state on the host
     if not 1 <= int(batch) <= 32:
@@ -290,7 +294,8 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
         t_group = time.time()
         if world > 1 or n_workers == 1:
             idx, hist, iters, secs, errors, step_t = _group_on_device(base_config, combinations, mesh_folder, batch,
-                                                                      local_rank if world > 1 else 0, tiles[rank], suppress_print)
+                                                                      local_rank if world > 1 else 0, tiles[rank], suppress_print,
+                                                                      mode)
             gathered = sweep.gather_results(len(combinations), S, len(names), idx, hist, iters, secs, errors)
         else:
             if mp.get_start_method(allow_none=True) != 'spawn':
@@ -298,7 +303,7 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
                     mp.set_start_method('spawn', force=True)
                 except RuntimeError:
                     pass
-            jobs = [(base_config, combinations, mesh_folder, batch, d, tiles[d], suppress_print) for d in range(n_workers)]
+            jobs = [(base_config, combinations, mesh_folder, batch, d, tiles[d], suppress_print, mode) for d in range(n_workers)]
             with mp.Pool(processes=n_workers, initializer=initialize_worker) as pool:
                 parts = pool.map(_device_worker, jobs)
             hist = np.full((len(combinations), S, len(names)), np.nan)
@@ -376,7 +381,7 @@ def main():
     parser.add_argument('--write-xdmf', action='store_true', help='Write XDMF output files (forces --mode per_run)')
     parser.add_argument('--verbose', action='store_true', help='Show detailed output during simulations')
     parser.add_argument('--num-processes', type=int, default=None, help='Number of GPU workers (default: all visible GPUs)')
-    parser.add_argument('--mode', choices=['ensemble', 'per_run'], default='ensemble')
+    parser.add_argument('--mode', choices=['auto', 'ensemble', 'serial', 'per_run'], default='auto')
     parser.add_argument('--batch', type=int, default=16, help='Variants per ensemble tile (1..32)')
     args = parser.parse_args()
 

@@ -177,6 +177,13 @@ class Simulation2D:
     def sample_tag(self, name="p_sample"):
         return int(self.mat_tag_map[name])
 
+    def set_conductivity(self, name, k):
+        """Re-assemble the operator with material ``name`` at conductivity ``k`` (sweep variants)."""
+        tags = [self.mat_tag_map[m.name] for m in self.materials]
+        kappa = [float(k) if m.name == name else m.properties["k"] for m in self.materials]
+        self.solver.set_materials(tags, kappa, [m.properties["rho_cv"] for m in self.materials])
+        self.solver.build_operator(self.dt, axisymmetric=True)
+
     def close(self):
         self.solver.close()
 

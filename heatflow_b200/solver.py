@@ -102,8 +102,16 @@ class HeatSolver:
 
     # -- inspection -----------------------------------------------------------------
     def set_recycle(self, max_vectors):
-        """Start every solve from the projection of its RHS onto the last `max_vectors` corrections."""
+        """Start every solve from the projection of its RHS onto the corrections of up to `max_vectors`
+        earlier solves of this simulation (dropped by ``set_state`` / ``build_operator``)."""
         _lib.check(self._L.hf_set_recycle(self._h, int(max_vectors)))
+
+    def on_chip(self):
+        """True when the time loop runs in the persistent on-chip PCG kernel (hf_get_solver_path)."""
+        rc = self._L.hf_get_solver_path(self._h)
+        if rc < 0:
+            _lib.check(rc)
+        return rc == 2
 
     def sizes(self):
         n, nnz = C.c_int32(), C.c_int64()

@@ -1,12 +1,17 @@
-"""Ensemble engine of ``parameter_sweep``: tiles of B variants per GPU, variants sharded across ranks.
+"""Execution engine of ``parameter_sweep``: tiles of B variants per GPU, variants sharded across ranks.
 
 The reference runs one OS process per parameter set, each re-reading the mesh, re-assembling and
 re-factorising (parameter_sweep.py:123-192, :436-438).  Here the variants of one width group
 (same mesh) differ only in the sample conductivity and the Gaussian heating width, so a rank
 
   * sets the mesh / pattern / base operator up once (``Simulation2D``),
-  * advances its variants in tiles of ``batch`` simulations with the batched multi-RHS kernels
-    (``hf_ens_create`` / ``hf_ens_run``), and
+  * advances its variants tile by tile - engine ``'ensemble'``: ``batch`` simulations at once through
+    the batched multi-RHS kernels (``hf_ens_create`` / ``hf_ens_run``), which read the operator once
+    for the whole tile (meshes that stream from HBM); engine ``'serial'``: one simulation after the
+    other through the single-simulation path, re-assembling only when the conductivity changes
+    (meshes that fit on chip: the persistent kernel is latency-bound, so batching buys nothing and
+    every simulation keeps the recycled-initial-guess speed-up); ``'auto'`` picks by
+    ``HeatSolver.on_chip()`` - and
   * hands its ``[P_local, S, n_watch]`` watcher histories to rank 0 in ONE final gather - the only
     collective of the sweep.
 
@@ -40,7 +45,41 @@ def plan_tiles(k_values, batch, world_size):
     return [cut[r::world_size] for r in range(world_size)]
 
 
-def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample"):
+def run_tiles_serial(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample"):
+    """``run_tiles`` through the single-simulation path: same arguments, same return value
+    (iters = PCG iterations of the variant itself, seconds = wall time of the variant)."""
+    s = sim.solver
+    S, W = sim.num_steps, len(watch_nodes)
+    idx_all, hist_all, it_all, sec_all, errors = [], [], [], [], {}
+    k_now = None
+    u0 = np.full(sim.n_dofs, sim.ic_temp)
+    for tile in tiles:
+        for i in np.asarray(tile, dtype=np.int64):
+            t0 = time.time()
+            try:
+                ki = float(np.asarray(k)[i])
+                if k_now != ki:
+                    k_now = None                      # a failed re-assembly must not be mistaken for this k
+                    sim.set_conductivity(sample_name, ki)
+                    k_now = ki
+                s.set_state(u0)
+                hist, iters, _ = s.run(sim.amps, sim.ic_temp, problem.gaussian_coeff(float(np.asarray(fwhm)[i])), watch_nodes)
+                its = int(iters.sum())
+            except Exception as exc:                   # recorded per run, as the reference does
+                errors[int(i)] = str(exc)
+                hist = np.full((S, W), np.nan)
+                its = -1
+            idx_all.append(int(i))
+            hist_all.append(hist)
+            it_all.append(its)
+            sec_all.append(time.time() - t0)
+    if not idx_all:
+        return (np.zeros(0, np.int64), np.zeros((0, S, W)), np.zeros(0, np.int64), np.zeros(0), errors)
+    return (np.asarray(idx_all, dtype=np.int64), np.stack(hist_all).reshape(len(idx_all), S, W),
+            np.asarray(it_all, dtype=np.int64), np.asarray(sec_all), errors)
+
+
+def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample", engine="ensemble"):
     """Advance every tile on ``sim.solver``'s device.
 
     ``fwhm`` / ``k``: arrays over ALL variants; ``tiles``: index arrays owned by this rank.
@@ -48,7 +87,11 @@ def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample"):
     variant's tile, summed over steps), seconds [P_local] (tile wall time / tile size), errors
     {index: message}).
     """
+    if engine not in ("auto", "ensemble", "serial"):
+        raise ValueError("engine must be 'auto', 'ensemble' or 'serial'")
     s = sim.solver
+    if engine == "serial" or (engine == "auto" and s.on_chip()):
+        return run_tiles_serial(sim, fwhm, k, tiles, watch_nodes, sample_name)
     S, W = sim.num_steps, len(watch_nodes)
     idx_all, hist_all, it_all, sec_all, errors = [], [], [], [], {}
     for tile in tiles:

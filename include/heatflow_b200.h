@@ -92,12 +92,14 @@ int hf_set_source(hf_ctx* ctx, const double* s);
  * graph, 2 = persistent cooperative kernel. */
 int hf_set_solver(hf_ctx* ctx, double rtol, int32_t max_iters, double warm, int32_t mode);
 
-/* Initial guess from the previous time steps: keep the corrections of the last max_vectors
- * solves (A-orthogonalised) and start every solve from the Galerkin projection of its
+/* Initial guess from the previous time steps: keep the corrections of up to max_vectors
+ * solves (A-orthogonalised; the basis is frozen once full) and start every solve from the Galerkin projection of its
  * right-hand side onto them.  The solver, its tolerance and therefore the converged answer are
  * unchanged (the reference re-uses its LU factors across steps in the same spirit,
- * run_with_diamond.py:389-394); 0 disables.  Memory: 2 * max_vectors * N doubles.  The basis is
- * dropped by hf_set_state and hf_build_operator. */
+ * run_with_diamond.py:389-394); 0 disables.  Memory: 2 * max_vectors * N doubles.  The basis
+ * belongs to one simulation: hf_set_state and hf_build_operator drop it (measured: a basis
+ * carried over to a simulation with other boundary data fills up with directions the new
+ * run does not use and costs more than it saves). */
 int hf_set_recycle(hf_ctx* ctx, int32_t max_vectors);
 
 /* One backward-Euler step (reference loop body, run_with_diamond.py:471-481):
@@ -119,6 +121,11 @@ int hf_run(hf_ctx* ctx, int32_t n_steps, const double* amp, double t_ic, double 
            int32_t* iters);
 
 int hf_sample(hf_ctx* ctx, int32_t n, const int32_t* nodes, double* out);
+
+/* Which PCG kernel hf_step / hf_run will use for the current operator and hf_set_solver mode:
+ * 2 = persistent on-chip kernel (the mesh fits in the SMs' shared memory), 1 = streaming kernel;
+ * < 0 on error. */
+int hf_get_solver_path(hf_ctx* ctx);
 
 /* Counters for benchmarking: stats[0] = device time of the step loop of the last hf_run /
  * hf_ens_run in ms (CUDA events on the context stream), stats[1] = kernels launched since

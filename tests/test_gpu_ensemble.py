@@ -105,17 +105,19 @@ def coarse_cfg_file(tmp_path, name, factor):
     return cfg, str(path)
 
 
-@pytest.mark.parametrize("name,factor", [("geballe_with_diamond", 8.0), ("geballe_no_diamond", 6.0)])
-def test_parameter_sweep_outputs_match_oracle(tmp_path, name, factor):
+@pytest.mark.parametrize("name,factor,mode", [("geballe_with_diamond", 8.0, "ensemble"), ("geballe_no_diamond", 6.0, "ensemble"),
+                                              ("geballe_with_diamond", 8.0, "auto"), ("geballe_no_diamond", 6.0, "serial")])
+def test_parameter_sweep_outputs_match_oracle(tmp_path, name, factor, mode):
     import parameter_sweep as psw
     from heatflow_b200.mesh_and_materials import read_msh
     cfg, cfg_path = coarse_cfg_file(tmp_path, name, factor)
     out, meshes = str(tmp_path / "sweep"), str(tmp_path / "meshes")
     width = float(cfg["mats"]["p_sample"]["z"])
     results, failed = psw.run_parameter_sweep(cfg_path, out, (2e-6, 5e-5), (2.0, 50.0), (width, width), (2, 3, 1),
-                                              base_mesh_folder=meshes, batch=4)
+                                              base_mesh_folder=meshes, batch=4, mode=mode)
     assert failed == [] and len(results) == 6
     meta = json.load(open(os.path.join(out, "sweep_metadata.json")))
+    assert meta["execution"]["mode"] == mode
     assert meta["total_runs"] == 6 and meta["k_values"] == np.logspace(np.log10(2.0), np.log10(50.0), 3).tolist()
     ok = pd.read_csv(os.path.join(out, "successful_runs.csv"))
     assert list(ok.columns) == ["run_id", "run_name", "fwhm", "k", "width", "output_dir", "runtime", "status", "error"]

@@ -239,7 +239,7 @@ def test_error_paths(small_nd):
 
 # ---- initial guess recycled from the previous solves (hf_set_recycle, the runners' default) ----
 @pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
-@pytest.mark.parametrize("cap", [128, 6], ids=["full-history", "ring-wraps"])
+@pytest.mark.parametrize("cap", [128, 6], ids=["full-history", "frozen-when-full"])
 def test_recycled_initial_guess_vs_oracle_every_step(mode, cap):
     c = build_case("geballe_with_diamond", 4.0)
     s = make_solver(c, warm=1.0, mode=mode, recycle=cap)
