@@ -20,38 +20,35 @@
 
 #include "hf_ctx.cuh"
 
-#define RC_SEG 128            // rows per warp of the dot-product kernel
+#define RC_SEG 1024           // rows per CTA of the dot-product kernel
 #define RC_WARPS 8
 
-// parts[k * nseg + seg] = sum over the 128 rows of segment `seg` of V[k][i] * v[i], k < m.
-// One warp per segment keeps v in registers and streams four basis vectors per round (16
-// independent 256-byte loads in flight per warp).
+// parts[k * nseg + seg] = sum over the 1024 rows of segment `seg` of V[k][i] * v[i], k < m.
+// One CTA per segment; every lane keeps its 32 values of v in registers (2 x 16 consecutive-pair
+// loads) and the warps share the basis vectors (warp w takes k = w, w + 8, ...), so each warp has
+// sixteen independent 512-byte loads in flight per basis vector and no barrier is needed.
 __global__ void __launch_bounds__(RC_WARPS * 32)
 k_rc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double* __restrict__ v,
           double* __restrict__ parts) {
-  const int lane = threadIdx.x & 31;
-  const int seg = blockIdx.x * RC_WARPS + (threadIdx.x >> 5);
-  if (seg >= nseg) return;
-  const size_t base = (size_t)seg * RC_SEG + lane;
-  double vv[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = blockIdx.x;
+  const size_t base = (size_t)seg * RC_SEG + 2 * lane;
+  double2 vv[16];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) vv[j] = v[base + 32 * j];
-  for (int k = 0; k < m; k += 4) {
-    double a[4][4];
+  for (int j = 0; j < 16; ++j) vv[j] = *reinterpret_cast<const double2*>(v + base + 64 * j);
+  for (int k = warp; k < m; k += RC_WARPS) {
+    const double* p = V + (size_t)k * ld + base;
+    double2 a[16];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const double* p = V + (size_t)min(k + t, m - 1) * ld + base;
+    for (int j = 0; j < 16; ++j) a[j] = __ldcs(reinterpret_cast<const double2*>(p + 64 * j));
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) a[t][j] = hf_ld_stream(p + 32 * j);
+    for (int j = 0; j < 16; ++j) {
+      s0 = fma(a[j].x, vv[j].x, s0);
+      s1 = fma(a[j].y, vv[j].y, s1);
     }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s = fma(a[t][j], vv[j], s);
-      s = hf_warp_sum(s);
-      if (lane == 0 && k + t < m) parts[(size_t)(k + t) * nseg + seg] = s;
-    }
+    const double s = hf_warp_sum(s0 + s1);
+    if (lane == 0) parts[(size_t)k * nseg + seg] = s;
   }
 }
 
@@ -214,7 +211,7 @@ int hf_rc_project(hf_ctx* c) {
     HF_CUDA(cudaMemcpyAsync(slotW, w.x.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
     return HF_OK;
   }
-  k_rc_dots<<<(rc.nseg + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.W.p, w.r.p, rc.parts.p);
+  k_rc_dots<<<rc.nseg, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.W.p, w.r.p, rc.parts.p);
   k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.parts.p, rc.inv.p, 1.0, rc.coef.p);
   HfCtrl* ctl = w.ctrl.p;
   k_rc_update<false><<<w.grid, HF_BLOCK, sizeof(double) * m, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, w.x.p,
@@ -235,7 +232,7 @@ int hf_rc_store(hf_ctx* c, const SellOp& op) {
   const int spc = HF_BLOCK / 32;
   k_rc_spmv<<<(op.nslices + spc - 1) / spc, HF_BLOCK, 0, c->stream>>>(op.view(), w.x.p, slotW, rc.d.p, rc.ad.p);
   if (m > 0) {
-    k_rc_dots<<<(rc.nseg + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.AW.p, rc.d.p, rc.parts.p);
+    k_rc_dots<<<rc.nseg, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.AW.p, rc.d.p, rc.parts.p);
     k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.parts.p, rc.inv.p, -1.0, rc.coef.p);
     c->stat_launches += 2;
   }

@@ -3,6 +3,9 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
+if os.environ.get("HF_DEV_LIB"):
+    from heatflow_b200 import _lib as _l
+    _l.LIB_PATH = os.path.abspath(os.environ["HF_DEV_LIB"])
 from helpers import build_case, make_solver, make_oracle
 
 def probe(name, scale, steps, caps, mode=0, check=True):
