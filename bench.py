@@ -128,23 +128,45 @@ def oracle_loop(c, steps, warmup):
     return t_loop, t_asm, t_fac, O
 
 
+def _reference_worker(job):
+    index, steps, warmup = job
+    os.environ["OMP_NUM_THREADS"] = "1"
+    c = build(index)
+    t_loop, t_asm, t_fac, _ = oracle_loop(c, steps, warmup)
+    return len(c.nodes), t_loop, t_asm, t_fac
+
+
 def run_reference(args, rank, world):
+    """CPU arm: the oracle port (scipy sparse LU) on the box's host cores.  Like our arm at N GPUs it runs N
+    independent simulations (sweep variant = index), one single-threaded process each - the reference's own
+    execution model (parameter_sweep.py:46-66, :436-438: an mp.Pool of single-threaded workers)."""
     if rank != 0:
         return
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    c = build(0)
-    n = len(c.nodes)
-    steps = min(args.steps, c.num_steps - args.warmup)
-    t_loop, t_asm, t_fac, _ = oracle_loop(c, steps, args.warmup)
-    value = n * steps / t_loop
+    nsim = max(1, args.gpus)
+    c0 = build(0)
+    steps = min(args.steps, c0.num_steps - args.warmup)
+    jobs = [(i, steps, args.warmup) for i in range(nsim)]
+    if nsim == 1:
+        res = [_reference_worker(jobs[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(processes=min(nsim, os.cpu_count() or 1)) as pool:
+            res = pool.map(_reference_worker, jobs)
+    n = res[0][0]
+    t_loop = max(r[1] for r in res)                    # the job ends when its slowest simulation does
+    value = nsim * n * steps / t_loop
+    cores = min(nsim, os.cpu_count() or 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "DOF-timesteps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_loop / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: 1 simulation, N={n} dofs, cfg mesh sizes, in-repo mesher"},
-        "cpu_baseline": {"value": value, "unit": "DOF-timesteps/s", "cores": 1, "kind": "port",
-                         "sample": f"{steps} time steps after {args.warmup} warm-up steps; scipy splu factorised once "
-                                   f"outside the timed loop (assembly {t_asm:.2f} s, factorisation {t_fac:.2f} s)"},
+        "config": {"workload": f"{WORKLOAD}: {nsim} independent simulation(s) (sweep variant = index), N={n} dofs each, "
+                               "cfg mesh sizes, in-repo mesher"},
+        "cpu_baseline": {"value": value, "unit": "DOF-timesteps/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} time steps after {args.warmup} warm-up steps per simulation, {nsim} simulation(s) in "
+                                   f"{cores} single-threaded process(es); scipy splu factorised once outside the timed loop "
+                                   f"(assembly {res[0][2]:.2f} s, factorisation {res[0][3]:.2f} s); host has {os.cpu_count()} cores"},
         "e2e": {"value": value, "unit": "DOF-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -170,17 +192,18 @@ def configured_solver(case, device, rtol, warm=0.0, mode=0, ordering="auto", rec
 
 
 def streaming_roofline(case, device, rtol, peak, peak_src, steps, traffic=None):
-    """k_pcg_iter timed inside a solve of `steps` time steps (CUDA events around the step loop)."""
+    """k_pcg_iter timed inside real solves: CUDA events on the solver stream around the PCG solve of every
+    time step (hf_set_profile), divided by the k_pcg_iter launches inside the brackets."""
     s = configured_solver(case, device, rtol, mode=1)
     n, nnz = s.sizes()
     s.set_state(np.full(n, case.ic))
     k0 = min(10, max(0, case.num_steps - steps - 1))
     s.run(case.amps[k0:k0 + 1], case.ic, case.coeff, [0])               # warm-up: graphs captured
-    l0 = s.stats()["launches"]
+    s.set_profile(True)
     _, iters, _ = s.run(case.amps[k0 + 1:k0 + 1 + steps], case.ic, case.coeff, [0])
-    st = s.stats()
-    launches = st["launches"] - l0
-    us = st["run_ms"] * 1e3 / max(1, launches)
+    solve_ms, launches = s.solve_profile()
+    s.set_profile(False)
+    us = solve_ms * 1e3 / max(1, launches)
     alg = iter_bytes(n, nnz)
     ms_flushed, _ = s.bench_kernels(reps=20, flush_l2=True)
     s.close()
@@ -188,9 +211,26 @@ def streaming_roofline(case, device, rtol, peak, peak_src, steps, traffic=None):
     return {"bound": "hbm", "kernel": "k_pcg_iter", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_us": us, "launches": int(launches),
             "pcg_iterations": int(iters.sum()), "n_dofs": n, "nnz": nnz,
-            "isolated_launch_us_l2_flushed": ms_flushed * 1e3, "peak_source": peak_src,
-            "how": f"CUDA events on the solver stream around {steps} time steps / kernels launched in between "
-                   "(every launch of the loop: per-step RHS kernels and early-exit launches after convergence included)"}
+            "isolated_launch_us_l2_flushed": ms_flushed * 1e3, "isolated_frac_l2_flushed": alg / (ms_flushed * 1e-3) / 1e9 / peak,
+            "peak_source": peak_src,
+            "how": f"CUDA events on the solver stream around the PCG solves of {steps} time steps / k_pcg_iter launches inside "
+                   "the brackets (launch gaps and the early-exit launches after convergence count against it); "
+                   "isolated_*: single launches with the L2 flushed in between"}
+
+
+def large_mesh_run(case, device, rtol, warm, recycle):
+    """BASELINE config #4: the whole konopkova run on the >= 1 M-dof mesh with the runner defaults."""
+    s = configured_solver(case, device, rtol, warm=warm, recycle=recycle)
+    n, nnz = s.sizes()
+    s.set_state(np.full(n, case.ic))
+    s.run(case.amps[:2], case.ic, case.coeff, [0])                      # warm-up: graphs captured
+    s.set_state(np.full(n, case.ic))
+    _, iters, _ = s.run(case.amps, case.ic, case.coeff, [0])
+    ms = s.stats()["run_ms"]
+    s.close()
+    return {"workload": f"konopkova refined, N={n} dofs, nnz={nnz}, {case.num_steps} steps, streaming kernel, "
+                        f"recycled initial guess {recycle} vectors", "value": n * case.num_steps / (ms * 1e-3),
+            "unit": "DOF-timesteps/s", "ms_per_step": ms / case.num_steps, "pcg_iterations_total": int(iters.sum())}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -239,6 +279,14 @@ def run_ours(args, rank, world, local_rank):
     final = s.get_state()                                  # D2H: N*8 bytes
     e2e_s = time.perf_counter() - t0
     barrier()
+
+    # ---- kernel timing pass for the roofline: CUDA events around every PCG solve (hf_set_profile)
+    s.set_profile(True)
+    s.set_state(u0)
+    _, iters_p, _ = s.run(c.amps[:steps], c.ic, c.coeff, watch)
+    solve_ms, solve_launches = s.solve_profile()
+    prof_run_ms = s.stats()["run_ms"]
+    s.set_profile(False)
 
     # ---- sweep tile: 16 (k, fwhm) variants of config #5 per GPU through the sweep engine's path for this mesh
     # (heatflow_b200/sweep.py: 'serial' when the mesh fits on chip, else the batched ensemble kernels);
@@ -350,6 +398,7 @@ def run_ours(args, rank, world, local_rank):
         cl = build_case("konopkova", 0.35)
         line["roofline_1m"] = streaming_roofline(cl, local_rank, args.rtol, peak, peak_src, steps=3,
                                                  traffic=traffic.get("k_pcg_iter_1m"))
+        line["konopkova_1m"] = large_mesh_run(cl, local_rank, args.rtol, args.warm_start, min(args.recycle, 64))
     # CPU baseline on this host (bounded sample)
     if not args.skip_cpu:
         cb_steps = min(20, steps)

@@ -64,6 +64,7 @@ extern "C" void hf_destroy(hf_ctx* c) {
   c->opMr.drop_graphs();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   cudaStream_t s = c->stream;
   delete c;
   cudaStreamDestroy(s);
@@ -843,7 +844,7 @@ static int finish_sync(hf_ctx* c, int* iters, double* relres) {
 
 // step_slot >= 0: fully asynchronous (persistent kernel only), iteration count goes to ws.step_iters[step_slot]
 static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double coeff, int* iters, double* relres,
-                       int step_slot) {
+                       int step_slot, int prof_slot = -1) {
   if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_step: operator not built");
   bool persist = false;
   HF_TRY(pick_persist(c, c->opA, &persist));
@@ -860,11 +861,18 @@ static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double
   HF_CUDA(cudaGetLastError());
   HF_TRY(hf_rc_project(c));
   HF_TRY(hf_pcg_prepare(c));
+  const bool prof = c->profile && prof_slot >= 0 && (size_t)(2 * prof_slot + 1) < c->prof_ev.size();
+  const unsigned long long l0 = c->stat_launches;
+  if (prof) HF_CUDA(cudaEventRecord(c->prof_ev[2 * prof_slot], c->stream));
   if (persist) {
     HF_TRY(hf_pcg_solve_async(c, c->opA, step_slot));
     if (step_slot < 0) HF_TRY(finish_sync(c, iters, relres));
   } else {
     HF_TRY(hf_pcg_solve(c, c->opA, iters, relres));
+  }
+  if (prof) {
+    HF_CUDA(cudaEventRecord(c->prof_ev[2 * prof_slot + 1], c->stream));
+    c->stat_solve_launches += c->stat_launches - l0;
   }
   HF_TRY(hf_rc_store(c, c->opA));
   k_step_finalize<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, w.x.p, c->opA.scale.p, c->u.p, c->uprev.p);
@@ -900,11 +908,19 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
     if (w.step_iters.n < (size_t)n_steps) HF_TRY(w.step_iters.alloc(n_steps, c->stream));
     HF_CUDA(cudaMemsetAsync(w.fail.p, 0, sizeof(int), c->stream));
   }
+  c->stat_solve_ms = 0.0;
+  c->stat_solve_launches = 0;
+  if (c->profile)
+    while (c->prof_ev.size() < (size_t)2 * n_steps) {
+      cudaEvent_t e;
+      HF_CUDA(cudaEventCreate(&e));
+      c->prof_ev.push_back(e);
+    }
   HF_CUDA(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < n_steps; ++s) {
     int it = 0;
     // XDMF field output needs the state on the host after every step; the copy is stream ordered
-    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr, persist ? s : -1));
+    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr, persist ? s : -1, s));
     if (iters && !persist) iters[s] = it;
     if (n_watch) c->stat_launches += 1;
     if (n_watch)
@@ -925,6 +941,12 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
   float ms = 0.f;
   HF_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->stat_run_ms = ms;
+  if (c->profile)
+    for (int s = 0; s < n_steps; ++s) {
+      float t = 0.f;
+      HF_CUDA(cudaEventElapsedTime(&t, c->prof_ev[2 * s], c->prof_ev[2 * s + 1]));
+      c->stat_solve_ms += t;
+    }
   if (persist && n_steps) {
     std::vector<int> hit(n_steps);
     int nfail = 0;
@@ -938,6 +960,19 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
     if (nfail) return hf_fail(HF_ERR_NOCONV, "PCG hit the iteration cap in " + std::to_string(nfail) + " of " +
                                                  std::to_string(n_steps) + " time steps");
   }
+  return HF_OK;
+}
+
+extern "C" int hf_set_profile(hf_ctx* c, int32_t on) {
+  if (!c) return hf_fail(HF_ERR_ARG, "null context");
+  c->profile = on != 0;
+  return HF_OK;
+}
+
+extern "C" int hf_get_solve_profile(hf_ctx* c, double* solve_ms, int64_t* solve_launches) {
+  if (!c || !solve_ms || !solve_launches) return hf_fail(HF_ERR_ARG, "hf_get_solve_profile: null argument");
+  *solve_ms = c->stat_solve_ms;
+  *solve_launches = (int64_t)c->stat_solve_launches;
   return HF_OK;
 }
 

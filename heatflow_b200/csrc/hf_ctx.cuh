@@ -206,6 +206,11 @@ struct hf_ctx {
   double stat_run_ms = 0.0, stat_relres = 0.0;
   unsigned long long stat_launches = 0, stat_iters = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // hf_set_profile: CUDA events around every PCG solve of hf_run (kernel time for the roofline numbers)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;
+  double stat_solve_ms = 0.0;
+  unsigned long long stat_solve_launches = 0;
   PcgWork ws;
   Recycle rc;
   DevBuf<double> hist;

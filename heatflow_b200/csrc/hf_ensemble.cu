@@ -62,6 +62,10 @@ struct EnsState {
   DevBuf<int> lc_off;                 // [nchunks+1] offsets of the chunks' column blocks (multiples of 8)
   DevBuf<unsigned short> lcol;        // local columns, chunk blocks padded to 16 bytes
   DevBuf<double2> bs;                 // {base0, S0} per CSR slot (16 bytes: any row range is TMA-aligned)
+  // recycled initial guess, one basis per variant (same scheme as hf_recycle.cu): slots of [nb] doubles in the
+  // [row, variant] layout; W = corrections, AW = D^-1 A_b W, inv[slot, b] = 1 / (w . A_b w)
+  int rc_cap = 0, rc_count = 0, rc_nseg = 0;
+  DevBuf<double> rc_W, rc_AW, rc_inv, rc_coef, rc_parts, rc_part_nn, rc_d, rc_ad;
   DevBuf<EnsCtrl> ctrl;
   EnsCtrl* h_ctrl = nullptr;          // pinned mirror
   DevBuf<double> hist, stage;
@@ -576,6 +580,167 @@ __global__ void k_ens_transpose(int N, const int* __restrict__ rank, const doubl
 }
 
 // ---------------------------------------------------------------------------------------
+// recycled initial guess (see hf_recycle.cu), one basis per variant.  All arrays use the [row, variant]
+// layout, so element idx belongs to variant idx & (B-1); inner products are taken in the A_b inner
+// product through the weight dg (the solver works with z = D^-1 r and w = D^-1 A p).
+// ---------------------------------------------------------------------------------------
+#define ERC_SEG 1024
+#define ERC_WARPS 8
+
+// parts[(k * nseg + seg) * B + b] = sum over the elements of variant b in segment seg of V[k] * v * wgt
+template <int LB>
+__global__ void __launch_bounds__(ERC_WARPS * 32)
+k_erc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double* __restrict__ v,
+           const double* __restrict__ wgt, double* __restrict__ parts) {
+  constexpr int B = 1 << LB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = blockIdx.x;
+  const size_t base = (size_t)seg * ERC_SEG + 2 * lane;
+  double2 vv[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const double2 a = *reinterpret_cast<const double2*>(v + base + 64 * j);
+    const double2 g = *reinterpret_cast<const double2*>(wgt + base + 64 * j);
+    vv[j] = make_double2(a.x * g.x, a.y * g.y);
+  }
+  for (int k = warp; k < m; k += ERC_WARPS) {
+    const double* p = V + (size_t)k * ld + base;
+    double2 a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = __ldcs(reinterpret_cast<const double2*>(p + 64 * j));
+    double s0 = 0.0, s1 = 0.0;          // variants (2 lane) & (B-1) and the next one: 64 j and 1024 seg are multiples of B
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      s0 = fma(a[j].x, vv[j].x, s0);
+      s1 = fma(a[j].y, vv[j].y, s1);
+    }
+#pragma unroll
+    for (int o = 16; o >= B / 2; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane < B / 2) {
+      double* out = parts + ((size_t)k * nseg + seg) * B + 2 * lane;
+      out[0] = s0;
+      out[1] = s1;
+    }
+  }
+}
+
+// coef[k, b] = sign * inv[k, b] * sum_seg parts[k, seg, b]   (one warp per k, fixed order)
+template <int LB>
+__global__ void __launch_bounds__(ERC_WARPS * 32)
+k_erc_coef(int m, int nseg, const double* __restrict__ parts, const double* __restrict__ inv, double sign,
+           double* __restrict__ coef) {
+  constexpr int B = 1 << LB;
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * ERC_WARPS + (threadIdx.x >> 5);
+  if (k >= m) return;
+  const int b = lane & (B - 1);
+  double s = 0.0;
+  for (int sg = lane >> LB; sg < nseg; sg += 32 >> LB) s += __ldcg(parts + ((size_t)k * nseg + sg) * B + b);
+#pragma unroll
+  for (int o = 16; o >= B; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane < B) coef[(size_t)k * B + lane] = sign * inv[(size_t)k * B + lane] * s;
+}
+
+// GS = false: a = x0, b = z0:  a += W c ; b -= AW c ; outW = a (null once the basis is frozen)
+// GS = true : a = d,  b = Ad, coef = -h:  outW = a + W coef ; outAW = b + AW coef ; per-variant partial
+//             sums of outW . outAW . wgt -> part[blockIdx.x * B + b]
+template <bool GS, int LB>
+__global__ void __launch_bounds__(HF_ET)
+k_erc_update(int m, size_t n, size_t ld, const double* __restrict__ W, const double* __restrict__ AW,
+             const double* __restrict__ coef, double* __restrict__ a, double* __restrict__ bv, double* __restrict__ outW,
+             double* __restrict__ outAW, const double* __restrict__ wgt, double* __restrict__ part) {
+  constexpr int B = 1 << LB;
+  extern __shared__ double s_coef[];
+  __shared__ double sh[HF_ET];
+  __shared__ double s_out[HF_EB];
+  for (int k = threadIdx.x; k < m * B; k += HF_ET) s_coef[k] = coef[k];
+  __syncthreads();
+  const int b = threadIdx.x & (B - 1);
+  double local = 0.0;
+  for (size_t i = (size_t)blockIdx.x * HF_ET + threadIdx.x; i < n; i += (size_t)gridDim.x * HF_ET) {
+    double ca0 = 0.0, ca1 = 0.0, cb0 = 0.0, cb1 = 0.0;
+    const double* w = W + i;
+    const double* aw = AW + i;
+    int k = 0;
+    for (; k + 4 <= m; k += 4) {
+      const double w0 = hf_ld_stream(w + (size_t)k * ld), w1 = hf_ld_stream(w + (size_t)(k + 1) * ld),
+                   w2 = hf_ld_stream(w + (size_t)(k + 2) * ld), w3 = hf_ld_stream(w + (size_t)(k + 3) * ld);
+      const double z0 = hf_ld_stream(aw + (size_t)k * ld), z1 = hf_ld_stream(aw + (size_t)(k + 1) * ld),
+                   z2 = hf_ld_stream(aw + (size_t)(k + 2) * ld), z3 = hf_ld_stream(aw + (size_t)(k + 3) * ld);
+      const double c0 = s_coef[k * B + b], c1 = s_coef[(k + 1) * B + b], c2 = s_coef[(k + 2) * B + b], c3 = s_coef[(k + 3) * B + b];
+      ca0 = fma(c0, w0, ca0);
+      ca1 = fma(c1, w1, ca1);
+      ca0 = fma(c2, w2, ca0);
+      ca1 = fma(c3, w3, ca1);
+      cb0 = fma(c0, z0, cb0);
+      cb1 = fma(c1, z1, cb1);
+      cb0 = fma(c2, z2, cb0);
+      cb1 = fma(c3, z3, cb1);
+    }
+    for (; k < m; ++k) {
+      const double ck = s_coef[k * B + b];
+      ca0 = fma(ck, hf_ld_stream(w + (size_t)k * ld), ca0);
+      cb0 = fma(ck, hf_ld_stream(aw + (size_t)k * ld), cb0);
+    }
+    const double ca = ca0 + ca1, cb = cb0 + cb1;
+    if (GS) {
+      const double d = a[i] + ca, ad = bv[i] + cb;
+      outW[i] = d;
+      outAW[i] = ad;
+      local = fma(d * wgt[i], ad, local);
+    } else {
+      const double x = a[i] + ca;
+      a[i] = x;
+      bv[i] -= cb;
+      if (outW) outW[i] = x;
+    }
+  }
+  if (GS) {
+    ens_block_sum<LB, HF_ET>(local, sh, s_out);
+    if (threadIdx.x < B) part[(size_t)blockIdx.x * B + threadIdx.x] = s_out[threadIdx.x];
+  }
+}
+
+// d = x - x0 and ad = D^-1 A_b d on free rows (0 on Dirichlet rows), one thread per (row, variant)
+template <int LB>
+__global__ void __launch_bounds__(HF_ET)
+k_erc_spmv(int N, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ base0,
+           const double* __restrict__ s0, const unsigned char* __restrict__ bcflag, const double* __restrict__ ks,
+           const double* __restrict__ dg, const double* __restrict__ x, const double* __restrict__ x0,
+           double* __restrict__ d, double* __restrict__ ad) {
+  constexpr int B = 1 << LB;
+  const size_t idx = (size_t)blockIdx.x * HF_ET + threadIdx.x;
+  const int i = (int)(idx >> LB), b = (int)(idx & (B - 1));
+  if (i >= N) return;
+  double dv = 0.0, av = 0.0;
+  if (!bcflag[i]) {
+    const double kb = ks[b];
+    double a0 = 0.0;
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const size_t j = ((size_t)col[k] << LB) + b;
+      a0 = fma(fma(kb, s0[k], base0[k]), x[j] - x0[j], a0);
+    }
+    dv = x[idx] - x0[idx];
+    av = a0 / dg[idx];
+  }
+  d[idx] = dv;
+  ad[idx] = av;
+}
+
+template <int LB>
+__global__ void k_erc_norm(int nparts, const double* __restrict__ part, double* __restrict__ inv, int slot) {
+  constexpr int B = 1 << LB;
+  const int b = threadIdx.x;
+  if (b >= B) return;
+  double nn = 0.0;
+  for (int i = 0; i < nparts; ++i) nn += __ldcg(part + (size_t)i * B + b);
+  inv[(size_t)slot * B + b] = (nn > 0.0 && isfinite(nn) && isfinite(1.0 / nn)) ? 1.0 / nn : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 #define ENS_DISPATCH(LBV, ...)                                 \
@@ -776,6 +941,53 @@ static int ens_solve(hf_ctx* c, EnsState* e, int* iters_out) {
   return HF_OK;
 }
 
+// Projection of the initial guess of all variants onto their recycled bases (hf_recycle.cu: hf_rc_project).
+static int ens_rc_project(hf_ctx* c, EnsState* e, size_t nb) {
+  if (e->rc_cap == 0) return HF_OK;
+  const int m = std::min(e->rc_count, e->rc_cap);
+  double* slotW = (m < e->rc_cap) ? e->rc_W.p + (size_t)m * nb : nullptr;
+  if (m == 0) {
+    HF_CUDA(cudaMemcpyAsync(slotW, e->x.p, sizeof(double) * nb, cudaMemcpyDeviceToDevice, c->stream));
+    return HF_OK;
+  }
+  const int B = e->B;
+  ENS_DISPATCH(e->LB, k_erc_dots<LB><<<e->rc_nseg, ERC_WARPS * 32, 0, c->stream>>>(m, e->rc_nseg, nb, e->rc_W.p, e->z.p, e->dg.p,
+                                                                                  e->rc_parts.p));
+  ENS_DISPATCH(e->LB, k_erc_coef<LB><<<(m + ERC_WARPS - 1) / ERC_WARPS, ERC_WARPS * 32, 0, c->stream>>>(m, e->rc_nseg, e->rc_parts.p,
+                                                                                                       e->rc_inv.p, 1.0, e->rc_coef.p));
+  ENS_DISPATCH(e->LB, k_erc_update<false, LB><<<e->grid, HF_ET, sizeof(double) * m * B, c->stream>>>(
+                          m, nb, nb, e->rc_W.p, e->rc_AW.p, e->rc_coef.p, e->x.p, e->z.p, slotW, nullptr, e->dg.p, nullptr));
+  c->stat_launches += 3;
+  HF_CUDA(cudaGetLastError());
+  return HF_OK;
+}
+
+// Store the A_b-orthogonalised correction of the solve that just finished (hf_recycle.cu: hf_rc_store).
+static int ens_rc_store(hf_ctx* c, EnsState* e, size_t nb) {
+  if (e->rc_cap == 0 || e->rc_count >= e->rc_cap) return HF_OK;
+  const int m = e->rc_count, B = e->B, N = c->N;
+  double* slotW = e->rc_W.p + (size_t)m * nb;
+  double* slotAW = e->rc_AW.p + (size_t)m * nb;
+  const unsigned blocks = (unsigned)(((size_t)N * B + HF_ET - 1) / HF_ET);
+  ENS_DISPATCH(e->LB, k_erc_spmv<LB><<<blocks, HF_ET, 0, c->stream>>>(N, c->rowptr.p, c->col.p, e->base0.p, e->s0.p, c->bcflag.p,
+                                                                     e->ks.p, e->dg.p, e->x.p, slotW, e->rc_d.p, e->rc_ad.p));
+  if (m > 0) {
+    // h = (A_b w_k) . d = sum AW_k * d * dg
+    ENS_DISPATCH(e->LB, k_erc_dots<LB><<<e->rc_nseg, ERC_WARPS * 32, 0, c->stream>>>(m, e->rc_nseg, nb, e->rc_AW.p, e->rc_d.p, e->dg.p,
+                                                                                    e->rc_parts.p));
+    ENS_DISPATCH(e->LB, k_erc_coef<LB><<<(m + ERC_WARPS - 1) / ERC_WARPS, ERC_WARPS * 32, 0, c->stream>>>(
+                            m, e->rc_nseg, e->rc_parts.p, e->rc_inv.p, -1.0, e->rc_coef.p));
+    c->stat_launches += 2;
+  }
+  ENS_DISPATCH(e->LB, k_erc_update<true, LB><<<e->grid, HF_ET, sizeof(double) * m * B, c->stream>>>(
+                          m, nb, nb, e->rc_W.p, e->rc_AW.p, e->rc_coef.p, e->rc_d.p, e->rc_ad.p, slotW, slotAW, e->dg.p, e->rc_part_nn.p));
+  ENS_DISPATCH(e->LB, k_erc_norm<LB><<<1, 32, 0, c->stream>>>(e->grid, e->rc_part_nn.p, e->rc_inv.p, m));
+  c->stat_launches += 3;
+  HF_CUDA(cudaGetLastError());
+  e->rc_count += 1;
+  return HF_OK;
+}
+
 extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic, int32_t n_watch,
                           const int32_t* watch_nodes, double* hist, int32_t* iters) {
   if (!c || !c->ens) return hf_fail(HF_ERR_STATE, "hf_ens_run: call hf_ens_create first");
@@ -791,6 +1003,25 @@ extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double 
     HF_TRY(e->watch.upload(wn.data(), n_watch, c->stream));
     if (e->hist.n < (size_t)B * n_steps * n_watch) HF_TRY(e->hist.alloc((size_t)B * n_steps * n_watch, c->stream));
   }
+  const size_t nbp = (size_t)e->nchunks * HF_EPAIRS;     // padded vector length (a multiple of ERC_SEG)
+  if (c->rc.cap > 0 && e->rc_cap == 0) {
+    size_t free_b = 0, total_b = 0;
+    HF_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t fit = (free_b / 2) / (16 * nbp);         // W + AW, at most half of the free memory
+    e->rc_cap = (int)std::min<size_t>({(size_t)c->rc.cap, fit, (size_t)(40960 / (8 * B))});   // coefficients live in shared memory
+    if (e->rc_cap > 0) {
+      e->rc_nseg = (int)(nbp / ERC_SEG);
+      HF_TRY(e->rc_W.alloc((size_t)e->rc_cap * nbp, c->stream));
+      HF_TRY(e->rc_AW.alloc((size_t)e->rc_cap * nbp, c->stream));
+      HF_TRY(e->rc_inv.alloc((size_t)e->rc_cap * B, c->stream));
+      HF_TRY(e->rc_coef.alloc((size_t)e->rc_cap * B, c->stream));
+      HF_TRY(e->rc_parts.alloc((size_t)e->rc_cap * e->rc_nseg * B, c->stream));
+      HF_TRY(e->rc_part_nn.alloc((size_t)e->grid * B, c->stream));
+      HF_TRY(e->rc_d.alloc(nbp, c->stream));
+      HF_TRY(e->rc_ad.alloc(nbp, c->stream));
+      e->rc_count = 0;
+    }
+  }
   HF_CUDA(cudaEventRecord(c->ev0, c->stream));
   for (int s = 0; s < n_steps; ++s) {
     if (c->n_gauss) {
@@ -805,8 +1036,10 @@ extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double 
                                                                         e->part.p, e->ctrl.p, c->rtol));
     c->stat_launches += 1;
     HF_CUDA(cudaGetLastError());
+    HF_TRY(ens_rc_project(c, e, nbp));
     int it = 0;
     HF_TRY(ens_solve(c, e, &it));
+    HF_TRY(ens_rc_store(c, e, nbp));
     if (iters) iters[s] = it;
     if (n_watch) {
       const int n = n_watch * B;

@@ -184,6 +184,16 @@ class HeatSolver:
         _lib.check(self._L.hf_get_stats(self._h, _lib.ptr(st)))
         return {"run_ms": st[0], "launches": int(st[1]), "iterations": int(st[2]), "relres": st[3]}
 
+    def set_profile(self, on=True):
+        """CUDA events around every PCG solve of ``run`` (see ``solve_profile``)."""
+        _lib.check(self._L.hf_set_profile(self._h, 1 if on else 0))
+
+    def solve_profile(self):
+        """(device ms inside the PCG solves of the last ``run``, solver kernels launched there)."""
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self._L.hf_get_solve_profile(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def project_gradient(self):
         g = np.empty((self.n, 2))
         it = C.c_int32()

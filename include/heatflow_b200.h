@@ -122,6 +122,14 @@ int hf_run(hf_ctx* ctx, int32_t n_steps, const double* amp, double t_ic, double 
 
 int hf_sample(hf_ctx* ctx, int32_t n, const int32_t* nodes, double* out);
 
+/* Kernel timing for the roofline numbers: with profiling on, hf_run brackets the PCG solve of every
+ * time step (the persistent kernel launch, or the streaming kernel launches of the step) with CUDA
+ * events on the context stream; hf_get_solve_profile returns their summed device time in ms and the
+ * number of solver kernels launched inside the brackets during the last hf_run.  Off by default (two
+ * event records per step). */
+int hf_set_profile(hf_ctx* ctx, int32_t on);
+int hf_get_solve_profile(hf_ctx* ctx, double* solve_ms, int64_t* solve_launches);
+
 /* Which PCG kernel hf_step / hf_run will use for the current operator and hf_set_solver mode:
  * 2 = persistent on-chip kernel (the mesh fits in the SMs' shared memory), 1 = streaming kernel;
  * < 0 on error. */

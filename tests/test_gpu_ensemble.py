@@ -157,3 +157,33 @@ def test_parameter_sweep_outputs_match_oracle(tmp_path, name, factor, mode):
         a = pd.read_csv(os.path.join(out2, r["run_name"], "watcher_points.csv"))
         b = pd.read_csv(os.path.join(out, r["run_name"], "watcher_points.csv"))
         assert np.abs(a[["pside", "oside"]].to_numpy() / b[["pside", "oside"]].to_numpy() - 1).max() <= 1e-11
+
+
+@pytest.mark.parametrize("ks,fw,cap", [
+    ([1.0, 10.0, 100.0], [1e-6, 1.3e-5, 1e-4], 64),                        # padded tile, full history
+    (list(np.logspace(0, 2, 16)), list(np.logspace(-6, -4, 16)[::-1]), 64),  # B = 16
+    (list(np.logspace(0, 2, 8)), list(np.logspace(-6, -4, 8)), 5),         # basis frozen after 5 solves
+])
+def test_ensemble_with_recycled_initial_guess_matches_oracle(wd, ks, fw, cap):
+    # per-variant recycled bases (hf_set_recycle applies to the ensemble too): same answers, fewer iterations
+    c = wd
+    S = 40
+    watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 3e-8, 0.0), (0.95e-6, 0.0), (0.0, 5e-6)])
+    coeffs = [problem.gaussian_coeff(f) for f in fw]
+    s0 = make_solver(c, warm=1.0, ordering="hilbert")
+    s0.ens_create(ks, coeffs, sample_tag(c))
+    _, it0 = s0.ens_run(c.amps[:S], c.ic, watch)
+    s0.close()
+    s = make_solver(c, warm=1.0, ordering="hilbert", recycle=cap)
+    s.ens_create(ks, coeffs, sample_tag(c))
+    hist, iters = s.ens_run(c.amps[:S], c.ic, watch)
+    u = s.ens_get_state()
+    for b, (k, f) in enumerate(zip(ks, fw)):
+        O = oracle_variant(c, k, f)
+        ohist, _ = O.run(S, watch)
+        assert np.abs(hist[b] / ohist - 1).max() <= RTOL_FIELD, (b, k, f)
+        assert np.abs(u[b] / O.u - 1).max() <= RTOL_FIELD, (b, k, f)
+    if cap >= S:
+        assert iters.sum() < 0.6 * it0.sum()
+    s.ens_destroy()
+    s.close()

@@ -18,7 +18,8 @@ Bs = [int(a) for a in sys.argv[4:]] or [4, 8, 16, 32]
 c = build_case(name, scale)
 n = len(c.nodes)
 tag = int(c.tags[[m.name for m in c.mats].index("p_sample")])
-s = make_solver(c, ordering=os.environ.get("HF_ORD", "hilbert"))
+s = make_solver(c, warm=float(os.environ.get("HF_WARM", "1")), ordering=os.environ.get("HF_ORD", "hilbert"),
+                recycle=int(os.environ.get("HF_RECYCLE", "0")))
 for B in Bs:
     ks = np.logspace(0, 2, 64)[20:20 + B]
     fw = np.logspace(-6, -4, 64)[10:10 + B]
