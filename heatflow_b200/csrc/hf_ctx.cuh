@@ -139,6 +139,7 @@ struct PcgWork {
   DevBuf<double> parts;                // [4][max chunks] per-CTA partial sums (streaming kernel)
   DevBuf<HfCtrl> ctrl;
   DevBuf<uint4> slots;                 // flag-with-data reduction slots (persistent kernel)
+  DevBuf<unsigned long long> acc, acc_prev;   // fixed-point reduction accumulators (persistent kernel)
   DevBuf<uint4> qpk;                   // [2][Npad] q = A p exchange packets (persistent kernel)
   DevBuf<unsigned> gen;                // barrier generation, monotonic across launches
   DevBuf<int> step_iters;              // per-step iteration counts written by the persistent kernel

@@ -32,7 +32,9 @@ struct PersistArgs {
   const double* r;      // in: rhat_0
   uint4* qpk;           // [2][Npad] q packets
   HfCtrl* c;            // thr, rr0 in; rr, itA, done out
-  uint4* slots;         // reduction slots
+  uint4* slots;         // reduction slots (HF_RED_MODE 0)
+  unsigned long long* acc;       // [2 sets][8 replicas][16 words] fixed-point accumulators (HF_RED_MODE 1)
+  unsigned long long* acc_prev;  // their values when the previous launch ended
   unsigned* gen;        // packet generation base, monotonic across launches
   const int2* cta_range;
   int* iters_out;       // may be null
@@ -137,6 +139,135 @@ __device__ __forceinline__ void hf_grid_wait(double (&out)[NV], uint4* slots, in
   for (int i = 0; i < NV; ++i) out[i] = sh[HF_PW * NV + i];
 }
 
+#ifndef HF_RED_MODE
+#define HF_RED_MODE 1    // 0: packet slots, CTA 0 reduces and broadcasts (two L2 trips); 1: fixed-point atomics (one trip)
+#endif
+#ifndef HF_NREP
+#define HF_NREP 8        // replicated accumulator lines (spreads the atomics of the G CTAs); <= 8 (4 polling lanes each)
+#endif
+#define HF_ACC_LINE 16   // 64-bit words per accumulator line (128 bytes)
+#define HF_FX_BITS 96    // a value below its bound 2^eb is accumulated as an integer multiple of 2^(eb - 96)
+#define HF_FX_MARGIN 12  // log2 of the safety factor on the magnitude estimates
+
+// ---- one-trip grid reduction with exact (order-independent) accumulation ------------------------------
+// Every CTA converts its partial sum t (|t| < 2^eb, eb known to all CTAs from shared scalars) to the
+// 96-bit fixed-point integer floor(t 2^(96-eb)) = hi 2^48 + lo and adds the two halves with 64-bit
+// integer atomics (RED, no return value) to one of HF_NREP accumulator lines.  Integer addition
+// commutes, so the total is independent of the arrival order: bit-reproducible like the ordered
+// packet tree, but with ONE store->load trip through L2 instead of two.  Each word carries its own
+// arrival count in its low 8 bits (every CTA adds (payload << 8) + 1), so a reader knows from the
+// word alone when all partials are in - no flag, fence or ordering between addresses is needed.
+// Words are never reset: readers work with the difference to the value the word had when the set was
+// last complete (kept in registers; carried from launch to launch through acc_prev).  Sets alternate
+// with the generation parity (a CTA can only add for generation g+2 after consuming g+1, which every
+// CTA contributes to only after consuming g).  A partial that is not finite or not below its bound
+// contributes a sentinel that turns the total into NaN in every CTA alike (the solve then fails loudly).
+struct FxState {
+  unsigned long long prev[2][2];   // [set][hi, lo] of this lane's chunk
+};
+
+__device__ __forceinline__ void hf_red_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void hf_ld2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// x < 2^hf_exp2(x) for a positive normal double (integer ops on the exponent field; 0, denormals and
+// non-finite values give out-of-range exponents, which end in the sentinel path / a harmless tiny scale)
+__device__ __forceinline__ int hf_exp2(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1022; }
+// t * 2^k without the software ldexp: two exact multiplications by powers of two (|k| <= 2000)
+__device__ __forceinline__ double hf_scale2(double t, int k) {
+  const int k1 = k / 2, k2 = k - k1;
+  return t * __hiloint2double((1023 + k1) << 20, 0) * __hiloint2double((1023 + k2) << 20, 0);
+}
+__device__ __forceinline__ int hf_clamp_exp(int e) { return max(-900, min(900, e)); }
+
+template <int NV>
+__device__ __forceinline__ void hf_fx_arrive(const double (&v)[NV], const int (&eb)[NV], unsigned long long* acc, unsigned gen,
+                                             double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double t = hf_warp_sum(v[i]);
+    if (lane == 0) sh[warp * NV + i] = t;
+  }
+  __syncthreads();
+  if (warp < NV) {
+    const double t = hf_warp_sum(lane < HF_PW ? sh[lane * NV + warp] : 0.0);
+    if (lane == 0) {
+      int e = eb[0];
+#pragma unroll
+      for (int i = 1; i < NV; ++i)
+        if (warp == i) e = eb[i];
+      const double x = hf_scale2(t, 48 - e);              // |x| < 2^48 when |t| < 2^e
+      long long hi;
+      unsigned long long lo;
+      if (fabs(x) < 281474976710656.0) {                  // 2^48; false for NaN / Inf as well
+        const double f = floor(x);
+        hi = (long long)f;
+        lo = (unsigned long long)((x - f) * 281474976710656.0);
+      } else {
+        hi = 1ll << 54;                                   // sentinel: the total decodes to NaN in every CTA
+        lo = 0ull;
+      }
+      unsigned long long* line = acc + ((size_t)(gen & 1u) * HF_NREP + (blockIdx.x % HF_NREP)) * HF_ACC_LINE + 2 * warp;
+      hf_red_add(line, ((unsigned long long)hi << 8) + 1ull);
+      hf_red_add(line + 1, (lo << 8) + 1ull);
+    }
+  }
+}
+
+// Warp 0 polls: lane l reads the 16-byte chunk (value l & 3, replica l >> 2).
+template <int NV>
+__device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV], const unsigned long long* acc, int G, unsigned gen,
+                                           double* red, FxState& st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
+  if (warp == 0) {
+    const int set = (int)(gen & 1u);
+    const int i = lane & 3, r = lane >> 2;
+    const int members = (r < G && r < HF_NREP) ? (G - 1 - r) / HF_NREP + 1 : 0;
+    const bool active = i < NV && members > 0;
+    const unsigned long long* chunk = acc + ((size_t)set * HF_NREP + r) * HF_ACC_LINE + 2 * i;
+    unsigned long long whi = 0ull, wlo = 0ull;
+    bool ok = !active;
+    for (;;) {
+      if (!ok) {
+        hf_ld2(chunk, whi, wlo);
+        ok = ((whi - st.prev[set][0]) & 0xffull) == (unsigned long long)members &&
+             ((wlo - st.prev[set][1]) & 0xffull) == (unsigned long long)members;
+      }
+      if (__all_sync(0xffffffffu, ok)) break;
+    }
+    long long shi = 0;
+    unsigned long long slo = 0ull;
+    if (active) {
+      shi = (long long)(whi - st.prev[set][0] - (unsigned long long)members) >> 8;
+      slo = (wlo - st.prev[set][1] - (unsigned long long)members) >> 8;
+      st.prev[set][0] = whi;
+      st.prev[set][1] = wlo;
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {                    // over the replicas: exact integer sums
+      shi += __shfl_xor_sync(0xffffffffu, shi, o);
+      slo += __shfl_xor_sync(0xffffffffu, slo, o);
+    }
+    if (lane < NV) {
+      int e = eb[0];
+#pragma unroll
+      for (int k = 1; k < NV; ++k)
+        if (lane == k) e = eb[k];
+      const bool bad = shi >= (1ll << 53) || shi <= -(1ll << 53);
+      const double val = hf_scale2(fma((double)shi, 281474976710656.0, (double)slo), e - HF_FX_BITS);
+      sh[HF_PW * NV + lane] = bad ? __longlong_as_double(0x7ff8000000000000ll) : val;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) out[i] = sh[HF_PW * NV + i];
+}
+
 template <int SPW>
 __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -202,6 +333,22 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
   int since_check = 0;
   double rr_ref = rr;
   bool done = !(rr > thr);
+#if HF_RED_MODE == 1
+  // magnitude estimates for the fixed-point reductions, identical in every CTA: ||p||^2 follows
+  // pp_n = rr_n + beta_n^2 pp_{n-1} (r_n is orthogonal to p_{n-1}); |p.q| <= L pp, q.q <= L^2 pp,
+  // |r.q| <= L sqrt(rr pp) with L = 16 >= ||Ahat||_inf (|ahat_ij| <= 1, at most 16 entries per row)
+  double pp = rr;
+  FxState fx;
+  {
+    const int ci = lane & 3, cr = lane >> 2;
+#pragma unroll
+    for (int set = 0; set < 2; ++set) {
+      const unsigned long long* q0 = P.acc_prev + ((size_t)set * HF_NREP + cr) * HF_ACC_LINE + 2 * ci;
+      fx.prev[set][0] = (warp == 0 && ci < 3 && cr < HF_NREP) ? q0[0] : 0ull;
+      fx.prev[set][1] = (warp == 0 && ci < 3 && cr < HF_NREP) ? q0[1] : 0ull;
+    }
+  }
+#endif
   while (!done && it < P.max_it) {
     ++gen;
     uint4* qout = P.qpk + (size_t)(it & 1) * P.npad;   // double buffered by iteration parity
@@ -223,7 +370,14 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
         d[2] = fma(acc, acc, d[2]);
       }
     }
+#if HF_RED_MODE == 1
+    const int e_pp = hf_exp2(pp), e_rr = hf_exp2(rr);
+    const int eb3[3] = {hf_clamp_exp(e_pp + 4 + HF_FX_MARGIN), hf_clamp_exp((e_rr + e_pp + 1) / 2 + 5 + HF_FX_MARGIN),
+                        hf_clamp_exp(e_pp + 8 + HF_FX_MARGIN)};
+    hf_fx_arrive<3>(d, eb3, P.acc, gen, red);
+#else
     hf_grid_arrive<3>(d, P.slots, gen, red);
+#endif
     // ---- halo q packets: warps >= 3 fetch them (all loads of a round in flight together),
     // re-poll until the generation matches and park the values in shared memory; this overlaps
     // the reduction, which warps 0..2 poll
@@ -256,7 +410,11 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
       }
     }
     double tot[3];
+#if HF_RED_MODE == 1
+    hf_fx_wait<3>(tot, eb3, P.acc, G, gen, red, fx);
+#else
     hf_grid_wait<3>(tot, P.slots, G, gen, red);
+#endif
     const double alpha = rr / tot[0];
     double rr_new = fma(alpha * alpha, tot[2], fma(-2.0 * alpha, tot[1], rr));
     ++since_check;
@@ -289,16 +447,29 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
     if (check) {
       // replace the recurrence value by the directly summed ||r||^2, then finish the p update
       ++gen;
-      hf_grid_arrive<1>(dd, P.slots, gen, red);
       double t1[1];
+#if HF_RED_MODE == 1
+      // ||r - alpha q||^2 <= 2 (rr + alpha^2 256 pp)
+      const int eb1[1] = {hf_clamp_exp(max(e_rr, 2 * hf_exp2(fabs(alpha)) + 8 + e_pp) + 2 + HF_FX_MARGIN)};
+      hf_fx_arrive<1>(dd, eb1, P.acc, gen, red);
+      hf_fx_wait<1>(t1, eb1, P.acc, G, gen, red, fx);
+#else
+      hf_grid_arrive<1>(dd, P.slots, gen, red);
       hf_grid_wait<1>(t1, P.slots, G, gen, red);
+#endif
       rr_new = t1[0];
       rr_ref = rr_new;
       since_check = 0;
       const double b2 = rr_new / rr;
       for (int i = tid; i < nr; i += HF_PT) sp[i] = fma(b2, sp[i], sr[i]);
       done = !(rr_new > thr);
+#if HF_RED_MODE == 1
+      pp = fma(b2 * b2, pp, fabs(rr_new));
+#endif
     }
+#if HF_RED_MODE == 1
+    else pp = fma(beta * beta, pp, fabs(rr_new));
+#endif
     rr = rr_new;
     ++it;
     __syncthreads();
@@ -306,12 +477,23 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
 #pragma unroll
   for (int k = 0; k < SPW; ++k)
     if (wid[k] >= 0) P.x[lo + idx[k]] = x[k];
+#if HF_RED_MODE == 1
+  if (blockIdx.x == 0 && warp == 0 && (lane & 3) < 3 && (lane >> 2) < HF_NREP) {   // accumulator values the next launch starts from
+    const int ci = lane & 3, cr = lane >> 2;
+#pragma unroll
+    for (int set = 0; set < 2; ++set) {
+      unsigned long long* q0 = P.acc_prev + ((size_t)set * HF_NREP + cr) * HF_ACC_LINE + 2 * ci;
+      q0[0] = fx.prev[set][0];
+      q0[1] = fx.prev[set][1];
+    }
+  }
+#endif
   if (blockIdx.x == 0 && tid == 0) {
     P.c->rr = rr;
     P.c->itA = it;
     P.c->done = done ? 1 : 0;
     if (P.iters_out) *P.iters_out = it;
-    if (!done) atomicAdd(P.fail, 1);
+    if (!done || !isfinite(rr)) atomicAdd(P.fail, 1);   // iteration cap, or a non-finite residual / reduction overflow
     *P.gen = gen;
   }
 }
@@ -372,6 +554,8 @@ int hf_persist_plan(hf_ctx* c, SellOp& op) {
       HF_TRY(w.slots.alloc((size_t)2 * (HF_MAX_GRID + 1) * HF_SLOT_STRIDE, c->stream));
       HF_TRY(w.gen.alloc(1, c->stream));
       HF_TRY(w.fail.alloc(1, c->stream));
+      HF_TRY(w.acc.alloc((size_t)2 * HF_NREP * HF_ACC_LINE, c->stream));
+      HF_TRY(w.acc_prev.alloc((size_t)2 * HF_NREP * HF_ACC_LINE, c->stream));
     }
     if (w.qpk.n < (size_t)2 * c->Npad) HF_TRY(w.qpk.alloc((size_t)2 * c->Npad, c->stream));
     HF_CUDA(cudaStreamSynchronize(c->stream));
@@ -393,6 +577,8 @@ int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot) {
   a.qpk = w.qpk.p;
   a.c = w.ctrl.p;
   a.slots = w.slots.p;
+  a.acc = w.acc.p;
+  a.acc_prev = w.acc_prev.p;
   a.gen = w.gen.p;
   a.cta_range = op.p_range.p;
   a.iters_out = (step_slot >= 0 && (size_t)step_slot < w.step_iters.n) ? w.step_iters.p + step_slot : nullptr;
