@@ -45,7 +45,12 @@ struct PersistArgs {
   int sz_cap;           // elements of the ghost range
 };
 
+#ifndef HF_PT
 #define HF_PT 256       // threads per CTA (1 CTA/SM => up to 255 registers/thread for the cached operator rows)
+#endif
+#ifndef HF_SPW
+#define HF_SPW 4        // sliced-ELL slices per warp = rows per thread
+#endif
 #define HF_PW (HF_PT / 32)
 #define HF_SLOT_STRIDE 8   // uint4 per slot: one 128-byte line each
 #define HF_MAX_GRID 160
@@ -518,7 +523,7 @@ int hf_persist_plan(hf_ctx* c, SellOp& op) {
   std::vector<int> sp(nsl + 1);
   HF_CUDA(cudaMemcpyAsync(sp.data(), op.slice_ptr.p, sizeof(int) * (nsl + 1), cudaMemcpyDeviceToHost, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
-  for (int spw = 4; spw <= 4; spw += 2) {
+  for (int spw = HF_SPW; spw <= HF_SPW; spw += 2) {
     const int per = HF_PW * spw;
     const int G = (nsl + per - 1) / per;
     if (G > c->sm_count || G > HF_MAX_GRID) continue;
@@ -548,7 +553,7 @@ int hf_persist_plan(hf_ctx* c, SellOp& op) {
     op.p_sz_cap = sz_cap;
     op.p_smem = bytes;
     HF_TRY(op.p_range.upload(range.data(), G, c->stream));
-    HF_CUDA(cudaFuncSetAttribute(k_pcg_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    HF_CUDA(cudaFuncSetAttribute(k_pcg_persist<HF_SPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     PcgWork& w = c->ws;
     if (w.slots.n < (size_t)2 * (HF_MAX_GRID + 1) * HF_SLOT_STRIDE) {
       HF_TRY(w.slots.alloc((size_t)2 * (HF_MAX_GRID + 1) * HF_SLOT_STRIDE, c->stream));
@@ -588,9 +593,9 @@ int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot) {
   a.mat_cap = op.p_mat_cap;
   a.sz_cap = op.p_sz_cap;
   void* args[] = {&a};
-  const void* fn = (const void*)k_pcg_persist<4>;
+  const void* fn = (const void*)k_pcg_persist<HF_SPW>;
   // the attribute is per function, not per operator: other operators / contexts may have lowered it
-  HF_CUDA(cudaFuncSetAttribute(k_pcg_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.p_smem));
+  HF_CUDA(cudaFuncSetAttribute(k_pcg_persist<HF_SPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op.p_smem));
   HF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(op.p_grid), dim3(HF_PT), args, op.p_smem, c->stream));
   c->stat_launches += 1;
   return HF_OK;
