@@ -860,12 +860,12 @@ static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double
                                                   w.r.p, w.ctrl.p);
   HF_CUDA(cudaGetLastError());
   HF_TRY(hf_rc_project(c));
-  HF_TRY(hf_pcg_prepare(c));
+  if (!persist) HF_TRY(hf_pcg_prepare(c));          // the persistent kernel sums the partials itself
   const bool prof = c->profile && prof_slot >= 0 && (size_t)(2 * prof_slot + 1) < c->prof_ev.size();
   const unsigned long long l0 = c->stat_launches;
   if (prof) HF_CUDA(cudaEventRecord(c->prof_ev[2 * prof_slot], c->stream));
   if (persist) {
-    HF_TRY(hf_pcg_solve_async(c, c->opA, step_slot));
+    HF_TRY(hf_pcg_solve_async(c, c->opA, step_slot, true));
     if (step_slot < 0) HF_TRY(finish_sync(c, iters, relres));
   } else {
     HF_TRY(hf_pcg_solve(c, c->opA, iters, relres));

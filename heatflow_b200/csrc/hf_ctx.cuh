@@ -149,11 +149,13 @@ struct PcgWork {
 };
 
 // Initial guess from the previous solves (hf_recycle.cu): Ahat-orthogonal corrections of up to `cap`
-// solves, kept as W, AW = Ahat W and inv[k] = 1 / (w_k . Ahat w_k); frozen once full.
+// solves, kept as W, AW = Ahat W and inv[k] = 1 / (w_k . Ahat w_k); frozen once full.  The correction of the
+// last solve waits in (d, ad) with its Gram-Schmidt coefficients hn until the next projection finalises it.
 struct Recycle {
-  int cap = 0, count = 0, nseg = 0;
+  int cap = 0, count = 0, nseg = 0, nn_parts = 0;
+  bool pending = false;
   size_t ld = 0;                       // row stride of W / AW (Npad rounded up to the dot-kernel segment)
-  DevBuf<double> W, AW, inv, coef, parts, part_nn, d, ad;
+  DevBuf<double> W, AW, inv, coef, hn, parts, part_nn, d, ad, x0;
 };
 
 struct EnsState;
@@ -270,7 +272,7 @@ __device__ __forceinline__ int hf_ld_stream(const int* p) {
 int hf_pcg_alloc(hf_ctx* c);
 int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out);
 int hf_persist_plan(hf_ctx* c, SellOp& op);
-int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot);
+int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts = false);
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out);
 int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out);
 void hf_ens_free(hf_ctx* c);

@@ -41,6 +41,8 @@ struct PersistArgs {
   int* fail;            // incremented when max_it is hit
   int max_it;
   int npad;
+  int nparts;           // > 0: thr and ||r_0||^2 are summed here from nparts partials of the control block
+  double rtol;          //      (saves the k_pcg_ctrl_init launch in front of every solve)
   int mat_cap;          // elements of the CTA operator slice held in shared memory
   int sz_cap;           // elements of the ghost range
 };
@@ -52,6 +54,7 @@ struct PersistArgs {
 #define HF_SPW 4        // sliced-ELL slices per warp = rows per thread
 #endif
 #define HF_PW (HF_PT / 32)
+static_assert(HF_PT == HF_BLOCK, "hf_sum_parts / hf_block_sum stride over HF_BLOCK threads");
 #define HF_SLOT_STRIDE 8   // uint4 per slot: one 128-byte line each
 #define HF_MAX_GRID 160
 #define HF_RR_CHECK 64  // iterations between direct recomputations of ||r||^2
@@ -318,8 +321,19 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
       x[k] = P.x[s * 32 + lane];
     }
   }
-  const double thr = P.c->thr;
-  double rr = P.c->rr;                 // ||r_0||^2, summed by k_pcg_ctrl_init
+  double thr, rr;                      // stopping threshold and ||r_0||^2
+  if (P.nparts > 0) {                  // same sums, in the same order, as k_pcg_ctrl_init (identical in every CTA)
+    const double bn2 = hf_sum_parts(P.c->part_bn, P.nparts, red);
+    rr = hf_sum_parts(P.c->part_rr[0], P.nparts, red);
+    thr = P.rtol * P.rtol * bn2;
+    if (blockIdx.x == 0 && tid == 0) {
+      P.c->bn2 = bn2;
+      P.c->thr = thr;
+    }
+  } else {
+    thr = P.c->thr;
+    rr = P.c->rr;
+  }
   unsigned gen = *P.gen;
   __syncthreads();
   // the first HF_WR entries of every own row are cached in registers (zero-padded)
@@ -572,7 +586,7 @@ int hf_persist_plan(hf_ctx* c, SellOp& op) {
 // Launch the whole solve; no host synchronisation.  step_slot >= 0 stores the iteration count
 // in ws.step_iters[step_slot].  On entry ws.x = xhat_0, ws.r = rhat_0 and the control block holds
 // thr and rr (= ||rhat_0||^2) from k_pcg_ctrl_init.
-int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot) {
+int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts) {
   PcgWork& w = c->ws;
   if (!op.p_spw) return hf_fail(HF_ERR_STATE, "persistent PCG kernel is not available for this mesh size");
   PersistArgs a;
@@ -589,6 +603,8 @@ int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot) {
   a.iters_out = (step_slot >= 0 && (size_t)step_slot < w.step_iters.n) ? w.step_iters.p + step_slot : nullptr;
   a.fail = w.fail.p;
   a.max_it = c->max_iters;
+  a.nparts = sum_parts ? w.grid : 0;
+  a.rtol = c->rtol;
   a.npad = c->Npad;
   a.mat_cap = op.p_mat_cap;
   a.sz_cap = op.p_sz_cap;

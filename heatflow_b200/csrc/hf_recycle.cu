@@ -5,15 +5,20 @@
 // solves found: all steps share the operator  Ahat = D^-1/2 (M + dt K) D^-1/2,  and the solutions
 // of a diffusion problem driven by one scalar amplitude stay close to a low-dimensional space.
 // This file keeps an Ahat-orthogonal basis  W = [w_1 .. w_m]  of the corrections the first m solves
-// computed, together with  AW = Ahat W  and  1 / (w_k . Ahat w_k):
-//   before the solve   x0 <- x0 + W c,  r0 <- r0 - AW c,  c_k = (w_k . r0) / (w_k . Ahat w_k)
+// computed, together with  AW = Ahat W  and  inv_k = 1 / (w_k . Ahat w_k):
+//   before the solve   x0 <- x0 + W c,  r0 <- r0 - AW c,  c_k = inv_k (w_k . r0)
 //                      (Galerkin projection: the error of x0 becomes Ahat-orthogonal to span W);
 //   after the solve    d = x - x0,  Ad = Ahat d (one SpMV, so that AW = Ahat W holds to rounding),
-//                      one Gram-Schmidt pass against W in the Ahat inner product, store (d, Ad).
+//                      h_k = inv_k (Ahat w_k . d),  w_{m+1} = d - W h,  Ahat w_{m+1} = Ad - AW h
+//                      (one Gram-Schmidt pass in the Ahat inner product; without it the computed
+//                      corrections are only orthogonal to ~1e-4 and the projection stops paying).
+// The Gram-Schmidt update is lazy: the pass over (W, AW) that applies h is the same pass that applies
+// c at the next solve, so a step streams 4 m N doubles (AW for h, W for c, W and AW for the fused
+// update) instead of 6 m N.  The new vector's coefficient follows from the raw dot products:
+//   w.r0 = d.r0 - sum h_k (w_k.r0),   w.Ahat w = d.Ad - sum h_k^2 / inv_k.
 // The solver itself is unchanged (Jacobi-PCG to the same tolerance on the same system): only the
 // starting point moves, so the converged answer is the same to the solver tolerance.  Measured on
-// geballe_with_diamond (N = 1.4e5, 100 steps): 223 instead of 620 iterations per step.
-// Cost per step: 6 m N doubles of streaming reads + 1 SpMV, a few percent of the iterations saved.
+// geballe_with_diamond (N = 1.4e5, 100 steps): 129 instead of 620 iterations per step.
 // All kernels are stream ordered; reductions add per-warp / per-CTA partials in a fixed order.
 #include <algorithm>
 #include <cmath>
@@ -23,13 +28,14 @@
 #define RC_SEG 1024           // rows per CTA of the dot-product kernel
 #define RC_WARPS 8
 
-// parts[k * nseg + seg] = sum over the 1024 rows of segment `seg` of V[k][i] * v[i], k < m.
+// parts[k * nseg + seg] = sum over the 1024 rows of segment `seg` of V[k][i] * v[i], k < m
+// (vector m_extra is read from `extra` instead of its slot).
 // One CTA per segment; every lane keeps its 32 values of v in registers (2 x 16 consecutive-pair
 // loads) and the warps share the basis vectors (warp w takes k = w, w + 8, ...), so each warp has
 // sixteen independent 512-byte loads in flight per basis vector and no barrier is needed.
 __global__ void __launch_bounds__(RC_WARPS * 32)
 k_rc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double* __restrict__ v,
-          double* __restrict__ parts) {
+          double* __restrict__ parts, int m_extra, const double* __restrict__ extra) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int seg = blockIdx.x;
   const size_t base = (size_t)seg * RC_SEG + 2 * lane;
@@ -37,7 +43,7 @@ k_rc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double
 #pragma unroll
   for (int j = 0; j < 16; ++j) vv[j] = *reinterpret_cast<const double2*>(v + base + 64 * j);
   for (int k = warp; k < m; k += RC_WARPS) {
-    const double* p = V + (size_t)k * ld + base;
+    const double* p = ((k == m_extra) ? extra : V + (size_t)k * ld) + base;   // the pending raw correction is not in a slot yet
     double2 a[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) a[j] = __ldcs(reinterpret_cast<const double2*>(p + 64 * j));
@@ -65,22 +71,78 @@ k_rc_coef(int m, int nseg, const double* __restrict__ parts, const double* __res
   if (lane == 0) coef[k] = sign * inv[k] * s;
 }
 
-// GS = false (before the solve):  a = x0, b = r0:   a += W c ; b -= AW c ; outW = a (x0 kept for the
-//                                 correction; null once the basis is frozen) ; partial sums of b.b  -> part[blockIdx.x]
-// GS = true  (after the solve):   a = d, b = Ad, coef = -h:  outW = a + W coef ; outAW = b + AW coef ;
-//                                 partial sums of outW.outAW -> part[blockIdx.x]
-template <bool GS>
+// Projection coefficients, one CTA.  t_k = sum_seg parts[k][seg] (one warp per k, fixed order);
+// c_k = inv_k t_k for the m finalised vectors.  With a pending raw correction (index m, Gram-Schmidt
+// coefficients hn_k = -h_k from the store phase, d.Ad partials in part_nn):
+//   w.r0 = t_m + sum hn_k t_k,  w.Ahat w = d.Ad - sum hn_k^2 / inv_k,  inv_m = 1 / (w.Ahat w),  c_m = inv_m (w.r0)
+// (inv_m = 0 when the correction is empty or not finite: the slot stays inert).
+#define RC_CT 1024
+__global__ void __launch_bounds__(RC_CT)
+k_rc_coef_project(int m, int pending, int nseg, const double* __restrict__ parts, double* __restrict__ inv,
+                  const double* __restrict__ hn, int nparts_nn, const double* __restrict__ part_nn, double* __restrict__ coef) {
+  __shared__ double s_t[RC_CT];        // m + pending <= cap + 1 <= RC_CT is checked on the host
+  __shared__ double s_red[3][RC_CT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mm = m + pending;
+  for (int k = warp; k < mm; k += RC_CT / 32) {
+    double s = 0.0;
+    for (int i = lane; i < nseg; i += 32) s += __ldcg(parts + (size_t)k * nseg + i);
+    s = hf_warp_sum(s);
+    if (lane == 0) s_t[k] = s;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < m; k += RC_CT) coef[k] = inv[k] * s_t[k];
+  if (!pending) return;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int k = threadIdx.x; k < m; k += RC_CT) {
+    const double h = hn[k], iv = inv[k];
+    s1 = fma(h, s_t[k], s1);
+    if (iv != 0.0) s2 = fma(h, h / iv, s2);
+  }
+  for (int i = threadIdx.x; i < nparts_nn; i += RC_CT) s3 += __ldcg(part_nn + i);
+  s1 = hf_warp_sum(s1);
+  s2 = hf_warp_sum(s2);
+  s3 = hf_warp_sum(s3);
+  if (lane == 0) {
+    s_red[0][warp] = s1;
+    s_red[1][warp] = s2;
+    s_red[2][warp] = s3;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int w = 0; w < RC_CT / 32; ++w) {
+      a1 += s_red[0][w];
+      a2 += s_red[1][w];
+      a3 += s_red[2][w];
+    }
+    const double nn = a3 - a2;
+    const double iv = (nn > 0.0 && isfinite(nn) && isfinite(1.0 / nn)) ? 1.0 / nn : 0.0;
+    inv[m] = iv;
+    coef[m] = iv * (s_t[m] + a1);
+  }
+}
+
+// Fused pass over (W, AW) before the solve:  a = x0, b = r0.
+//   PENDING: finalise the raw correction (d, ad) of the previous solve as vector m:
+//            w = d + W hn,  aw = ad + AW hn  -> slot m of W / AW
+//   a += W c (+ c_m w) ;  b -= AW c (+ c_m aw) ;  x0save = a (null once the basis is frozen) ;
+//   partial sums of b.b -> part[blockIdx.x]
+template <bool PENDING>
 __global__ void __launch_bounds__(HF_BLOCK)
-k_rc_update(int m, int n, size_t ld, const double* __restrict__ W, const double* __restrict__ AW,
-            const double* __restrict__ coef, double* __restrict__ a, double* __restrict__ b, double* __restrict__ outW,
-            double* __restrict__ outAW, double* __restrict__ part) {
-  extern __shared__ double s_coef[];
+k_rc_apply(int m, int n, size_t ld, double* __restrict__ W, double* __restrict__ AW, const double* __restrict__ coef,
+           const double* __restrict__ hn, const double* __restrict__ d, const double* __restrict__ ad, double* __restrict__ a,
+           double* __restrict__ b, double* __restrict__ x0save, double* __restrict__ part) {
+  extern __shared__ double s_c[];      // c[0..m] then hn[0..m)
   __shared__ double sh[HF_BLOCK / 32];
-  for (int k = threadIdx.x; k < m; k += HF_BLOCK) s_coef[k] = coef[k];
+  double* s_h = s_c + m + 1;
+  for (int k = threadIdx.x; k <= m; k += HF_BLOCK) s_c[k] = (k < m || PENDING) ? coef[k] : 0.0;
+  if (PENDING)
+    for (int k = threadIdx.x; k < m; k += HF_BLOCK) s_h[k] = hn[k];
   __syncthreads();
   double local = 0.0;
   for (int i = blockIdx.x * HF_BLOCK + threadIdx.x; i < n; i += gridDim.x * HF_BLOCK) {
-    double ca0 = 0.0, ca1 = 0.0, cb0 = 0.0, cb1 = 0.0;
+    double ca0 = 0.0, ca1 = 0.0, cb0 = 0.0, cb1 = 0.0, ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
     const double* w = W + i;
     const double* aw = AW + i;
     int k = 0;
@@ -89,7 +151,7 @@ k_rc_update(int m, int n, size_t ld, const double* __restrict__ W, const double*
                    w2 = hf_ld_stream(w + (size_t)(k + 2) * ld), w3 = hf_ld_stream(w + (size_t)(k + 3) * ld);
       const double z0 = hf_ld_stream(aw + (size_t)k * ld), z1 = hf_ld_stream(aw + (size_t)(k + 1) * ld),
                    z2 = hf_ld_stream(aw + (size_t)(k + 2) * ld), z3 = hf_ld_stream(aw + (size_t)(k + 3) * ld);
-      const double c0 = s_coef[k], c1 = s_coef[k + 1], c2 = s_coef[k + 2], c3 = s_coef[k + 3];
+      const double c0 = s_c[k], c1 = s_c[k + 1], c2 = s_c[k + 2], c3 = s_c[k + 3];
       ca0 = fma(c0, w0, ca0);
       ca1 = fma(c1, w1, ca1);
       ca0 = fma(c2, w2, ca0);
@@ -98,69 +160,88 @@ k_rc_update(int m, int n, size_t ld, const double* __restrict__ W, const double*
       cb1 = fma(c1, z1, cb1);
       cb0 = fma(c2, z2, cb0);
       cb1 = fma(c3, z3, cb1);
+      if (PENDING) {
+        const double h0 = s_h[k], h1 = s_h[k + 1], h2 = s_h[k + 2], h3 = s_h[k + 3];
+        ga0 = fma(h0, w0, ga0);
+        ga1 = fma(h1, w1, ga1);
+        ga0 = fma(h2, w2, ga0);
+        ga1 = fma(h3, w3, ga1);
+        gb0 = fma(h0, z0, gb0);
+        gb1 = fma(h1, z1, gb1);
+        gb0 = fma(h2, z2, gb0);
+        gb1 = fma(h3, z3, gb1);
+      }
     }
     for (; k < m; ++k) {
-      const double ck = s_coef[k];
-      ca0 = fma(ck, hf_ld_stream(w + (size_t)k * ld), ca0);
-      cb0 = fma(ck, hf_ld_stream(aw + (size_t)k * ld), cb0);
+      const double wk = hf_ld_stream(w + (size_t)k * ld), zk = hf_ld_stream(aw + (size_t)k * ld);
+      ca0 = fma(s_c[k], wk, ca0);
+      cb0 = fma(s_c[k], zk, cb0);
+      if (PENDING) {
+        ga0 = fma(s_h[k], wk, ga0);
+        gb0 = fma(s_h[k], zk, gb0);
+      }
     }
-    const double ca = ca0 + ca1, cb = cb0 + cb1;
-    if (GS) {
-      const double d = a[i] + ca, ad = b[i] + cb;
-      outW[i] = d;
-      outAW[i] = ad;
-      local = fma(d, ad, local);
-    } else {
-      const double x = a[i] + ca, r = b[i] - cb;
-      a[i] = x;
-      b[i] = r;
-      if (outW) outW[i] = x;
-      local = fma(r, r, local);
+    double ca = ca0 + ca1, cb = cb0 + cb1;
+    if (PENDING) {
+      const double wm = d[i] + (ga0 + ga1), awm = ad[i] + (gb0 + gb1);
+      W[(size_t)m * ld + i] = wm;
+      AW[(size_t)m * ld + i] = awm;
+      ca = fma(s_c[m], wm, ca);
+      cb = fma(s_c[m], awm, cb);
     }
+    const double x = a[i] + ca, r = b[i] - cb;
+    a[i] = x;
+    b[i] = r;
+    if (x0save) x0save[i] = x;
+    local = fma(r, r, local);
   }
   const double tot = hf_block_sum(local, sh);
   if (threadIdx.x == 0) part[blockIdx.x] = tot;
 }
 
-// d = x - x0 and Ad = Ahat d in one pass (sliced-ELL, one warp per slice; the gathers hit L2)
+// d = x - x0, ad = Ahat d and the partial sums of d.ad in one pass (sliced-ELL, one warp per slice;
+// the gathers hit L2)
 __global__ void __launch_bounds__(HF_BLOCK)
 k_rc_spmv(SellView A, const double* __restrict__ x, const double* __restrict__ x0, double* __restrict__ d,
-          double* __restrict__ ad) {
+          double* __restrict__ ad, double* __restrict__ part_nn) {
+  __shared__ double sh[HF_BLOCK / 32];
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * (HF_BLOCK / 32) + (threadIdx.x >> 5);
-  if (s >= A.nslices) return;
-  const int b0 = A.slice_ptr[s];
-  const int w = (A.slice_ptr[s + 1] - b0) >> 5;
-  const int* cp = A.col + b0 + lane;
-  const double* vp = A.val + b0 + lane;
-  double acc0 = 0.0, acc1 = 0.0;
-  int k = 0;
-  for (; k + 2 <= w; k += 2) {
-    const int c0 = cp[k * 32], c1 = cp[(k + 1) * 32];
-    const double v0 = vp[k * 32], v1 = vp[(k + 1) * 32];
-    acc0 = fma(v0, x[c0] - x0[c0], acc0);
-    acc1 = fma(v1, x[c1] - x0[c1], acc1);
+  double local = 0.0;
+  if (s < A.nslices) {
+    const int b0 = A.slice_ptr[s];
+    const int w = (A.slice_ptr[s + 1] - b0) >> 5;
+    const int* cp = A.col + b0 + lane;
+    const double* vp = A.val + b0 + lane;
+    double acc0 = 0.0, acc1 = 0.0;
+    int k = 0;
+    for (; k + 2 <= w; k += 2) {
+      const int c0 = cp[k * 32], c1 = cp[(k + 1) * 32];
+      const double v0 = vp[k * 32], v1 = vp[(k + 1) * 32];
+      acc0 = fma(v0, x[c0] - x0[c0], acc0);
+      acc1 = fma(v1, x[c1] - x0[c1], acc1);
+    }
+    if (k < w) {
+      const int c0 = cp[k * 32];
+      acc0 = fma(vp[k * 32], x[c0] - x0[c0], acc0);
+    }
+    const int i = s * HF_SLICE + lane;
+    const double di = x[i] - x0[i], adi = acc0 + acc1;
+    d[i] = di;
+    ad[i] = adi;
+    local = di * adi;
   }
-  if (k < w) {
-    const int c0 = cp[k * 32];
-    acc0 = fma(vp[k * 32], x[c0] - x0[c0], acc0);
-  }
-  const int i = s * HF_SLICE + lane;
-  d[i] = x[i] - x0[i];
-  ad[i] = acc0 + acc1;
-}
-
-// inv[slot] = 1 / (w . Ahat w), 0 when the correction is empty or not finite (slot stays inert)
-__global__ void __launch_bounds__(HF_BLOCK) k_rc_norm(int nparts, const double* __restrict__ part, double* __restrict__ inv, int slot) {
-  __shared__ double sh[HF_BLOCK / 32];
-  const double nn = hf_sum_parts(part, nparts, sh);
-  if (threadIdx.x == 0) inv[slot] = (nn > 0.0 && isfinite(nn) && isfinite(1.0 / nn)) ? 1.0 / nn : 0.0;
+  const double tot = hf_block_sum(local, sh);
+  if (threadIdx.x == 0) part_nn[blockIdx.x] = tot;
 }
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-void hf_rc_reset(hf_ctx* c) { c->rc.count = 0; }
+void hf_rc_reset(hf_ctx* c) {
+  c->rc.count = 0;
+  c->rc.pending = false;
+}
 
 static int rc_alloc(hf_ctx* c) {
   Recycle& rc = c->rc;
@@ -168,20 +249,23 @@ static int rc_alloc(hf_ctx* c) {
   if (rc.ld == ld && rc.W.n == (size_t)rc.cap * ld) return HF_OK;
   rc.ld = ld;
   rc.nseg = (int)(ld / RC_SEG);
+  rc.nn_parts = (c->Npad / HF_SLICE + HF_BLOCK / 32 - 1) / (HF_BLOCK / 32);
   HF_TRY(rc.W.alloc((size_t)rc.cap * ld, c->stream));
   HF_TRY(rc.AW.alloc((size_t)rc.cap * ld, c->stream));
-  HF_TRY(rc.inv.alloc(rc.cap, c->stream));
-  HF_TRY(rc.coef.alloc(rc.cap, c->stream));
-  HF_TRY(rc.parts.alloc((size_t)rc.cap * rc.nseg, c->stream));
-  HF_TRY(rc.part_nn.alloc(HF_MAX_PART, c->stream));
+  HF_TRY(rc.inv.alloc(rc.cap + 1, c->stream));
+  HF_TRY(rc.coef.alloc(rc.cap + 1, c->stream));
+  HF_TRY(rc.hn.alloc(rc.cap + 1, c->stream));
+  HF_TRY(rc.parts.alloc((size_t)(rc.cap + 1) * rc.nseg, c->stream));
+  HF_TRY(rc.part_nn.alloc(rc.nn_parts, c->stream));
   HF_TRY(rc.d.alloc(ld, c->stream));
   HF_TRY(rc.ad.alloc(ld, c->stream));
+  HF_TRY(rc.x0.alloc(ld, c->stream));
   hf_rc_reset(c);
   return HF_OK;
 }
 
 extern "C" int hf_set_recycle(hf_ctx* c, int32_t max_vectors) {
-  if (!c || max_vectors < 0 || max_vectors > 4096) return hf_fail(HF_ERR_ARG, "hf_set_recycle: bad arguments");
+  if (!c || max_vectors < 0 || max_vectors >= RC_CT) return hf_fail(HF_ERR_ARG, "hf_set_recycle: max_vectors must be in [0, 1023]");
   cudaSetDevice(c->device);
   Recycle& rc = c->rc;
   if (max_vectors != rc.cap) {
@@ -195,7 +279,8 @@ extern "C" int hf_set_recycle(hf_ctx* c, int32_t max_vectors) {
 }
 
 // ws.x = x0, ws.r = r0 = bhat - Ahat x0 and ctrl.part_rr[0][0 .. ws.grid) hold the caller's values;
-// on return they hold the projected ones and the next free slot of W keeps x0.
+// on return they hold the projected ones and rc.x0 keeps x0.  A correction left pending by the
+// previous solve is finalised on the way (it becomes vector `count`).
 // Once `cap` corrections are stored the basis is frozen: every vector is Ahat-orthogonal to the others
 // and carries a direction the later solutions keep using (the low-order Krylov vectors of the time
 // stepping), so evicting the oldest one costs a full-length solve per step (measured); the late
@@ -205,42 +290,45 @@ int hf_rc_project(hf_ctx* c) {
   if (rc.cap == 0) return HF_OK;
   HF_TRY(rc_alloc(c));
   PcgWork& w = c->ws;
-  const int m = std::min(rc.count, rc.cap);
-  double* slotW = (m < rc.cap) ? rc.W.p + (size_t)m * rc.ld : nullptr;
-  if (m == 0) {
-    HF_CUDA(cudaMemcpyAsync(slotW, w.x.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
+  const int m = rc.count, pend = rc.pending ? 1 : 0;
+  const bool record = m + pend < rc.cap;          // this solve's correction will be stored
+  if (m + pend == 0) {
+    HF_CUDA(cudaMemcpyAsync(rc.x0.p, w.x.p, sizeof(double) * c->Npad, cudaMemcpyDeviceToDevice, c->stream));
     return HF_OK;
   }
-  k_rc_dots<<<rc.nseg, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.W.p, w.r.p, rc.parts.p);
-  k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.parts.p, rc.inv.p, 1.0, rc.coef.p);
+  k_rc_dots<<<rc.nseg, RC_WARPS * 32, 0, c->stream>>>(m + pend, rc.nseg, rc.ld, rc.W.p, w.r.p, rc.parts.p, pend ? m : -1, rc.d.p);
+  k_rc_coef_project<<<1, RC_CT, 0, c->stream>>>(m, pend, rc.nseg, rc.parts.p, rc.inv.p, rc.hn.p, rc.nn_parts, rc.part_nn.p,
+                                                rc.coef.p);
   HfCtrl* ctl = w.ctrl.p;
-  k_rc_update<false><<<w.grid, HF_BLOCK, sizeof(double) * m, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, w.x.p,
-                                                                          w.r.p, slotW, nullptr, &ctl->part_rr[0][0]);
+  const size_t smem = sizeof(double) * (2 * (size_t)m + 1);
+  if (pend)
+    k_rc_apply<true><<<w.grid, HF_BLOCK, smem, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, rc.hn.p, rc.d.p, rc.ad.p,
+                                                            w.x.p, w.r.p, record ? rc.x0.p : nullptr, &ctl->part_rr[0][0]);
+  else
+    k_rc_apply<false><<<w.grid, HF_BLOCK, smem, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, rc.hn.p, rc.d.p, rc.ad.p,
+                                                             w.x.p, w.r.p, record ? rc.x0.p : nullptr, &ctl->part_rr[0][0]);
   c->stat_launches += 3;
   HF_CUDA(cudaGetLastError());
+  rc.count = m + pend;
+  rc.pending = false;
   return HF_OK;
 }
 
-// ws.x = converged xhat; stores the Ahat-orthogonalised correction of this solve in the next free slot.
+// ws.x = converged xhat: d = x - x0, Ad and the Gram-Schmidt coefficients against the stored basis;
+// the vector itself is finalised by the next hf_rc_project.
 int hf_rc_store(hf_ctx* c, const SellOp& op) {
   Recycle& rc = c->rc;
   if (rc.cap == 0 || rc.count >= rc.cap) return HF_OK;
   PcgWork& w = c->ws;
   const int m = rc.count;
-  double* slotW = rc.W.p + (size_t)m * rc.ld;
-  double* slotAW = rc.AW.p + (size_t)m * rc.ld;
-  const int spc = HF_BLOCK / 32;
-  k_rc_spmv<<<(op.nslices + spc - 1) / spc, HF_BLOCK, 0, c->stream>>>(op.view(), w.x.p, slotW, rc.d.p, rc.ad.p);
+  k_rc_spmv<<<rc.nn_parts, HF_BLOCK, 0, c->stream>>>(op.view(), w.x.p, rc.x0.p, rc.d.p, rc.ad.p, rc.part_nn.p);
+  c->stat_launches += 1;
   if (m > 0) {
-    k_rc_dots<<<rc.nseg, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.AW.p, rc.d.p, rc.parts.p);
-    k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.parts.p, rc.inv.p, -1.0, rc.coef.p);
+    k_rc_dots<<<rc.nseg, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.ld, rc.AW.p, rc.d.p, rc.parts.p, -1, nullptr);
+    k_rc_coef<<<(m + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, c->stream>>>(m, rc.nseg, rc.parts.p, rc.inv.p, -1.0, rc.hn.p);
     c->stat_launches += 2;
   }
-  k_rc_update<true><<<w.grid, HF_BLOCK, sizeof(double) * m, c->stream>>>(m, c->Npad, rc.ld, rc.W.p, rc.AW.p, rc.coef.p, rc.d.p,
-                                                                         rc.ad.p, slotW, slotAW, rc.part_nn.p);
-  k_rc_norm<<<1, HF_BLOCK, 0, c->stream>>>(w.grid, rc.part_nn.p, rc.inv.p, m);
-  c->stat_launches += 3;
   HF_CUDA(cudaGetLastError());
-  rc.count += 1;
+  rc.pending = true;
   return HF_OK;
 }
