@@ -241,6 +241,7 @@ def run_ours(args, rank, world, local_rank):
         raise RuntimeError("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("HF_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     c = build(rank)
     n = len(c.nodes)
