@@ -612,6 +612,7 @@ extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
   HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valA0.p));
   HF_TRY(hf_build_sell(c, c->valA0, true, c->opA, &c->valA));
   HF_TRY(hf_persist_plan(c, c->opA));
+  if (!c->opA.p_spw) HF_TRY(hf_patch_plan(c, c->opA));
   c->valM1.release();
   c->op_built = true;
   c->proj_built = false;
@@ -724,7 +725,7 @@ extern "C" int hf_set_source(hf_ctx* c, const double* s) {
 
 extern "C" int hf_set_solver(hf_ctx* c, double rtol, int32_t max_iters, double warm, int32_t mode) {
   if (!c) return hf_fail(HF_ERR_ARG, "null context");
-  if (!(rtol > 0.0) || max_iters <= 0 || mode < 0 || mode > 2) return hf_fail(HF_ERR_ARG, "hf_set_solver: bad arguments");
+  if (!(rtol > 0.0) || max_iters <= 0 || mode < 0 || mode > 3) return hf_fail(HF_ERR_ARG, "hf_set_solver: bad arguments");
   c->rtol = rtol;
   c->max_iters = max_iters;
   c->warm = warm;
@@ -818,10 +819,18 @@ __global__ void k_sample(int n, const int* __restrict__ nodes, const double* __r
 
 // 0 = streaming graph chunks (host polls), 1 = persistent single-launch kernel
 static int pick_persist(hf_ctx* c, const SellOp& op, bool* persist) {
-  if (c->mode == 2 && !op.p_spw)
-    return hf_fail(HF_ERR_STATE, "solver mode 2 (persistent kernel) requested but the mesh does not fit on chip");
-  *persist = (c->mode == 2) || (c->mode == 0 && op.p_spw != 0);
+  if (c->mode == 3 && !op.pp_rpt) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));   // forced: plan on demand
+  const bool fits = op.p_spw != 0 || op.pp_rpt != 0;     // contiguous-range kernel or patch kernel
+  if ((c->mode == 2 && !fits) || (c->mode == 3 && !op.pp_rpt))
+    return hf_fail(HF_ERR_STATE, "an on-chip PCG kernel was requested (solver mode 2 / 3) but the mesh does not fit on chip");
+  *persist = (c->mode >= 2) || (c->mode == 0 && fits);
   return HF_OK;
+}
+
+// one cooperative launch per solve: the contiguous-range kernel when its plan exists, else the patch kernel
+static int solve_on_chip(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts) {
+  if (op.p_spw && c->mode != 3) return hf_pcg_solve_async(c, op, step_slot, sum_parts);
+  return hf_patch_solve_async(c, op, step_slot, sum_parts);
 }
 
 // Synchronous completion of a persistent solve: read the control-block header.
@@ -865,7 +874,7 @@ static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double
   const unsigned long long l0 = c->stat_launches;
   if (prof) HF_CUDA(cudaEventRecord(c->prof_ev[2 * prof_slot], c->stream));
   if (persist) {
-    HF_TRY(hf_pcg_solve_async(c, c->opA, step_slot, true));
+    HF_TRY(solve_on_chip(c, c->opA, step_slot, true));
     if (step_slot < 0) HF_TRY(finish_sync(c, iters, relres));
   } else {
     HF_TRY(hf_pcg_solve(c, c->opA, iters, relres));
@@ -1105,6 +1114,7 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, 1, vals.p));
     HF_TRY(hf_build_sell(c, vals, false, c->opMr, nullptr));
     HF_TRY(hf_persist_plan(c, c->opMr));
+    if (!c->opMr.p_spw) HF_TRY(hf_patch_plan(c, c->opMr));
     HF_TRY(c->proj_b.alloc((size_t)2 * c->Npad, c->stream));
     HF_TRY(c->proj_g.alloc((size_t)2 * c->N, c->stream));
     c->proj_built = true;
@@ -1126,7 +1136,7 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     bool persist = false;
     HF_TRY(pick_persist(c, c->opMr, &persist));
     if (persist) {
-      HF_TRY(hf_pcg_solve_async(c, c->opMr, -1));
+      HF_TRY(solve_on_chip(c, c->opMr, -1, false));
       HF_TRY(finish_sync(c, &it, nullptr));
     } else {
       HF_TRY(hf_pcg_solve(c, c->opMr, &it, nullptr));

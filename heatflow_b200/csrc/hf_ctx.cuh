@@ -116,6 +116,12 @@ struct SellOp {
   int p_spw = 0, p_grid = 0, p_mat_cap = 0, p_sz_cap = 0;
   size_t p_smem = 0;
   DevBuf<int2> p_range;                // per CTA: [lo, hi) column range of its rows
+  // plan of the patch-based persistent kernel (hf_patch.cu); pp_rpt == 0 => not eligible
+  int pp_rpt = 0, pp_grid = 0, pp_mat_cap = 0, pp_halo_cap = 0;
+  size_t pp_smem = 0;
+  DevBuf<unsigned short> pp_lcol;      // local columns for chunks of 256 * pp_rpt rows, sliced-ELL order
+  DevBuf<int> pp_halo_ptr, pp_halo_idx;
+  DevBuf<unsigned char> pp_pub;        // rows whose q packet some other CTA reads
   // patch decomposition (streaming kernel)
   int R = 0, nchunks = 0, halo_max = 0, mat_cap = 0, halo_cap = 0, nstages = 0;
   size_t stage_bytes = 0;
@@ -273,6 +279,8 @@ int hf_pcg_alloc(hf_ctx* c);
 int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out);
 int hf_persist_plan(hf_ctx* c, SellOp& op);
 int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts = false);
+int hf_patch_plan(hf_ctx* c, SellOp& op);
+int hf_patch_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts = false);
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out);
 int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out);
 void hf_ens_free(hf_ctx* c);

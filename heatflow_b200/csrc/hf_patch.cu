@@ -1,0 +1,396 @@
+// heatflow_b200 - persistent cooperative Jacobi-PCG on compact patches (sm_100a).
+//
+// Same algorithm and communication scheme as hf_persist.cu (one launch per solve, q = Ahat p halo
+// packets, one exact fixed-point grid reduction per iteration), for meshes whose 148 x 1024-row
+// contiguous ghost ranges no longer fit on chip (reference meshes: 2e5 - 4e5 nodes).  With the
+// Hilbert node order a CTA's R = 256 x RPT rows form a compact 2-D patch whose halo is a short list
+// (~4 sqrt(R) rows instead of two full mesh rows), so per row the CTA keeps
+//   operator   8 B value + 2 B local column per stored entry       (~85 B, sliced-ELL padding included)
+//   vectors    r, p on own + halo rows, q on halo rows              (~18 B)
+// in shared memory and x in registers: up to R = 2560 rows per SM, 148 x 2560 = 3.8e5 dofs on chip.
+// The streaming kernel (hf_pcg.cu) needs ~17-21 us per iteration at these sizes (L2-resident, bound
+// by launch and chunk latency); this kernel needs ~4-6 us.
+// Only rows that appear in another CTA's halo list publish their q packet.
+#include <algorithm>
+#include <cmath>
+
+#include "hf_ctx.cuh"
+#include "hf_persist.cuh"
+
+struct PatchArgs {
+  int nslices;
+  const int* slice_ptr;          // sliced-ELL offsets (SellOp)
+  const double* val;             // sliced-ELL values (SellOp)
+  const unsigned short* lcol;    // local columns for chunks of R rows: [0, R) own, R + h halo
+  const int* halo_ptr;           // [G + 1]
+  const int* halo_idx;           // global rows of the halo entries
+  const unsigned char* pub;      // [Npad] 1 = the row is in some CTA's halo list
+  double* x;                     // in: xhat_0, out: xhat
+  const double* r;               // in: rhat_0
+  uint4* qpk;                    // [2][Npad] q packets
+  HfCtrl* c;
+  unsigned long long* acc;       // fixed-point accumulators (shared with k_pcg_persist)
+  unsigned long long* acc_prev;
+  unsigned* gen;
+  int* iters_out;
+  int* fail;
+  int max_it, npad, nparts;
+  double rtol;
+  int mat_cap, halo_cap;
+};
+
+template <int RPT>
+__global__ void __launch_bounds__(HF_PT, 1) k_pcg_patch(PatchArgs P) {
+  constexpr int R = HF_PT * RPT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sval = reinterpret_cast<double*>(smem_raw);
+  double* sp = sval + P.mat_cap;                 // p: own rows [0, R), halo [R, R + nh)
+  double* sr = sp + R + P.halo_cap;              // r, same layout
+  double* sqh = sr + R + P.halo_cap;             // validated halo q values
+  double* red = sqh + P.halo_cap;                // reduction scratch: 2 x (HF_PW*3 + 3)
+  int* shal = reinterpret_cast<int*>(red + 2 * (HF_PW * 3 + 3) + 2);   // halo rows (global indices)
+  unsigned short* scol = reinterpret_cast<unsigned short*>(shal + P.halo_cap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, nsl = P.nslices;
+  const int f = blockIdx.x * (R / 32);
+  const int fend = min(f + R / 32, nsl);
+  const int e0 = P.slice_ptr[min(f, nsl)], e1 = P.slice_ptr[fend];
+  const int lo = blockIdx.x * R;
+  const int hp = P.halo_ptr[blockIdx.x];
+  const int nh = P.halo_ptr[blockIdx.x + 1] - hp;
+  for (int i = tid; i < e1 - e0; i += HF_PT) {
+    sval[i] = P.val[e0 + i];
+    scol[i] = P.lcol[e0 + i];
+  }
+  for (int i = tid; i < R; i += HF_PT) {
+    const double rv = (lo + i < P.npad) ? P.r[lo + i] : 0.0;
+    sr[i] = rv;
+    sp[i] = rv;                                  // p_0 = r_0
+  }
+  for (int h = tid; h < nh; h += HF_PT) {
+    const int g = P.halo_idx[hp + h];
+    shal[h] = g;
+    const double rv = P.r[g];
+    sr[R + h] = rv;
+    sp[R + h] = rv;
+  }
+  int base[RPT], wid[RPT];
+  double x[RPT], q[RPT];
+  unsigned pubmask = 0u;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int s = f + warp * RPT + k;
+    base[k] = 0;
+    wid[k] = -1;                                 // marks "no slice"
+    x[k] = q[k] = 0.0;
+    if (s < nsl) {
+      const int b0 = P.slice_ptr[s];
+      base[k] = b0 - e0 + lane;
+      wid[k] = (P.slice_ptr[s + 1] - b0) >> 5;
+      x[k] = P.x[s * 32 + lane];
+      if (P.pub[s * 32 + lane]) pubmask |= 1u << k;
+    }
+  }
+  double thr, rr;                                // stopping threshold and ||r_0||^2
+  if (P.nparts > 0) {                            // same sums, in the same order, as k_pcg_ctrl_init
+    const double bn2 = hf_sum_parts(P.c->part_bn, P.nparts, red);
+    rr = hf_sum_parts(P.c->part_rr[0], P.nparts, red);
+    thr = P.rtol * P.rtol * bn2;
+    if (blockIdx.x == 0 && tid == 0) {
+      P.c->bn2 = bn2;
+      P.c->thr = thr;
+    }
+  } else {
+    thr = P.c->thr;
+    rr = P.c->rr;
+  }
+  unsigned gen = *P.gen;
+  __syncthreads();
+
+  int it = 0;
+  int since_check = 0;
+  double rr_ref = rr;
+  bool done = !(rr > thr);
+  double pp = rr;                                // magnitude estimate of ||p||^2, see hf_persist.cu
+  FxState fx;
+  {
+    const int ci = lane & 3, cr = lane >> 2;
+#pragma unroll
+    for (int set = 0; set < 2; ++set) {
+      const unsigned long long* q0 = P.acc_prev + ((size_t)set * HF_NREP + cr) * HF_ACC_LINE + 2 * ci;
+      fx.prev[set][0] = (warp == 0 && ci < 3 && cr < HF_NREP) ? q0[0] : 0ull;
+      fx.prev[set][1] = (warp == 0 && ci < 3 && cr < HF_NREP) ? q0[1] : 0ull;
+    }
+  }
+  while (!done && it < P.max_it) {
+    ++gen;
+    uint4* qout = P.qpk + (size_t)(it & 1) * P.npad;   // double buffered by iteration parity
+    // ---- q = A p on the own rows (operator and p from shared memory); publish boundary rows; partial dots
+    double d[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      if (wid[k] >= 0) {
+        const int w = wid[k], b = base[k];
+        double a0 = 0.0, a1 = 0.0;
+        int kk = 0;
+        for (; kk + 2 <= w; kk += 2) {
+          const int c0 = scol[b + kk * 32], c1 = scol[b + (kk + 1) * 32];
+          const double v0 = sval[b + kk * 32], v1 = sval[b + (kk + 1) * 32];
+          a0 = fma(v0, sp[c0], a0);
+          a1 = fma(v1, sp[c1], a1);
+        }
+        if (kk < w) a0 = fma(sval[b + kk * 32], sp[scol[b + kk * 32]], a0);
+        const double acc = a0 + a1;
+        q[k] = acc;
+        const int i = (warp * RPT + k) * 32 + lane;
+        if (pubmask & (1u << k)) hf_pkt_store(qout + lo + i, acc, gen);
+        const double pv = sp[i], rv = sr[i];
+        d[0] = fma(pv, acc, d[0]);
+        d[1] = fma(rv, acc, d[1]);
+        d[2] = fma(acc, acc, d[2]);
+      }
+    }
+    const int e_pp = hf_exp2(pp), e_rr = hf_exp2(rr);
+    const int eb3[3] = {hf_clamp_exp(e_pp + 4 + HF_FX_MARGIN), hf_clamp_exp((e_rr + e_pp + 1) / 2 + 5 + HF_FX_MARGIN),
+                        hf_clamp_exp(e_pp + 8 + HF_FX_MARGIN)};
+    hf_fx_arrive<3>(d, eb3, P.acc, gen, red);
+    // ---- halo q packets: warps >= 1 fetch them while warp 0 polls the reduction
+    if (warp >= 1) {
+      constexpr int NP = HF_PT - 32;
+      for (int h0 = tid - 32; h0 < nh; h0 += 4 * NP) {
+        uint4 hq[4];
+        bool need[4];
+        int g[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          need[t] = (h0 + t * NP) < nh;
+          g[t] = need[t] ? shal[h0 + t * NP] : 0;
+        }
+        bool pending;
+        do {
+          pending = false;
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (need[t]) hq[t] = hf_pkt_load(qout + g[t]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (need[t]) {
+              if (hf_pkt_ok(hq[t], gen)) {
+                need[t] = false;
+                sqh[h0 + t * NP] = hf_pkt_val(hq[t]);
+              } else {
+                pending = true;
+              }
+            }
+        } while (pending);
+      }
+    }
+    double tot[3];
+    hf_fx_wait<3>(tot, eb3, P.acc, G, gen, red, fx);
+    const double alpha = rr / tot[0];
+    double rr_new = fma(alpha * alpha, tot[2], fma(-2.0 * alpha, tot[1], rr));
+    ++since_check;
+    const bool check = (since_check >= HF_RR_CHECK) || !(rr_new > thr) || (rr_new < 1e-4 * rr_ref);
+    const double beta = check ? 0.0 : rr_new / rr;
+    // ---- own rows: x += alpha p ; r -= alpha q ; p = r + beta p (deferred when beta is not final)
+    double dd[1] = {0.0};
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      if (wid[k] >= 0) {
+        const int i = (warp * RPT + k) * 32 + lane;
+        const double pv = sp[i];
+        x[k] = fma(alpha, pv, x[k]);
+        const double rv = fma(-alpha, q[k], sr[i]);
+        sr[i] = rv;
+        dd[0] = fma(rv, rv, dd[0]);
+        if (!check) sp[i] = fma(beta, pv, rv);
+      }
+    }
+    // ---- halo rows: the same update with the neighbours' q (bit-identical to the owner's)
+    for (int h = tid; h < nh; h += HF_PT) {
+      const double rv = fma(-alpha, sqh[h], sr[R + h]);
+      sr[R + h] = rv;
+      if (!check) sp[R + h] = fma(beta, sp[R + h], rv);
+    }
+    if (check) {
+      ++gen;
+      double t1[1];
+      const int eb1[1] = {hf_clamp_exp(max(e_rr, 2 * hf_exp2(fabs(alpha)) + 8 + e_pp) + 2 + HF_FX_MARGIN)};
+      hf_fx_arrive<1>(dd, eb1, P.acc, gen, red);
+      hf_fx_wait<1>(t1, eb1, P.acc, G, gen, red, fx);
+      rr_new = t1[0];
+      rr_ref = rr_new;
+      since_check = 0;
+      const double b2 = rr_new / rr;
+      for (int i = tid; i < R + nh; i += HF_PT) sp[i] = fma(b2, sp[i], sr[i]);
+      done = !(rr_new > thr);
+      pp = fma(b2 * b2, pp, fabs(rr_new));
+    } else {
+      pp = fma(beta * beta, pp, fabs(rr_new));
+    }
+    rr = rr_new;
+    ++it;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < RPT; ++k)
+    if (wid[k] >= 0) P.x[lo + (warp * RPT + k) * 32 + lane] = x[k];
+  if (blockIdx.x == 0 && warp == 0 && (lane & 3) < 3 && (lane >> 2) < HF_NREP) {
+    const int ci = lane & 3, cr = lane >> 2;
+#pragma unroll
+    for (int set = 0; set < 2; ++set) {
+      unsigned long long* q0 = P.acc_prev + ((size_t)set * HF_NREP + cr) * HF_ACC_LINE + 2 * ci;
+      q0[0] = fx.prev[set][0];
+      q0[1] = fx.prev[set][1];
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    P.c->rr = rr;
+    P.c->itA = it;
+    P.c->done = done ? 1 : 0;
+    if (P.iters_out) *P.iters_out = it;
+    if (!done || !isfinite(rr)) atomicAdd(P.fail, 1);
+    *P.gen = gen;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+// SELL-ordered 16-bit local columns for chunks of R rows from the CSR-ordered ones
+__global__ void k_patch_lcol(int N, int Npad, int R, const int* __restrict__ rowptr, const int* __restrict__ slice_ptr,
+                             const unsigned short* __restrict__ lcol_csr, unsigned short* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npad) return;
+  const int s = i / HF_SLICE, lane = i % HF_SLICE;
+  const int base = slice_ptr[s];
+  const int w = (slice_ptr[s + 1] - base) / HF_SLICE;
+  int len = 0, r0 = 0;
+  if (i < N) {
+    r0 = rowptr[i];
+    len = rowptr[i + 1] - r0;
+  }
+  for (int k = 0; k < w; ++k) out[base + k * HF_SLICE + lane] = (k < len) ? lcol_csr[r0 + k] : (unsigned short)(i % R);
+}
+
+static size_t patch_smem_bytes(int R, int mat_cap, int halo_cap) {
+  return sizeof(double) * ((size_t)mat_cap + 2 * ((size_t)R + halo_cap) + halo_cap + 2 * (HF_PW * 3 + 3) + 2) +
+         sizeof(int) * (size_t)halo_cap + sizeof(unsigned short) * (size_t)mat_cap;
+}
+
+template <int RPT>
+static int patch_set_smem(size_t bytes) {
+  HF_CUDA(cudaFuncSetAttribute(k_pcg_patch<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return HF_OK;
+}
+static int patch_set_smem_rpt(int rpt, size_t bytes) {
+  switch (rpt) {
+    case 4: return patch_set_smem<4>(bytes);
+    case 6: return patch_set_smem<6>(bytes);
+    case 8: return patch_set_smem<8>(bytes);
+    default: return patch_set_smem<10>(bytes);
+  }
+}
+
+// Decide rows per thread / grid / shared-memory layout; pp_rpt = 0 when the mesh does not fit.
+int hf_patch_plan(hf_ctx* c, SellOp& op) {
+  op.pp_rpt = 0;
+  const int nsl = op.nslices;
+  if (nsl == 0 || c->h_rowptr.empty()) return HF_OK;
+  int coop = 0, max_smem = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+  if (!coop) return HF_OK;
+  std::vector<int> sp(nsl + 1);
+  HF_CUDA(cudaMemcpyAsync(sp.data(), op.slice_ptr.p, sizeof(int) * (nsl + 1), cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  static const int kRpt[4] = {4, 6, 8, 10};
+  for (int t = 0; t < 4; ++t) {
+    const int rpt = kRpt[t], R = HF_PT * rpt;
+    const int G = (c->Npad + R - 1) / R;
+    if (G > c->sm_count || G > HF_MAX_GRID) continue;
+    int mat_cap = 0;
+    for (int b = 0; b < G; ++b) {
+      const int f = std::min(b * (R / 32), nsl), fe = std::min(f + R / 32, nsl);
+      mat_cap = std::max(mat_cap, sp[fe] - sp[f]);
+    }
+    std::vector<int> hptr, hidx;
+    std::vector<unsigned short> lcol;
+    int halo_max = 0;
+    if (hf_build_patches(c, R, hptr, hidx, lcol, &halo_max) != HF_OK) continue;
+    mat_cap = (mat_cap + 7) & ~7;
+    const int halo_cap = (halo_max + 3) & ~3;
+    const size_t bytes = patch_smem_bytes(R, mat_cap, halo_cap);
+    if (bytes > (size_t)max_smem) continue;
+    // rows that some other chunk reads publish their q packets
+    std::vector<unsigned char> pub(c->Npad, 0);
+    for (int g : hidx) pub[g] = 1;
+    if (hidx.empty()) hidx.push_back(0);
+    hptr.resize(G + 1, hptr.empty() ? 0 : hptr.back());
+    DevBuf<unsigned short> lcol_csr;
+    HF_TRY(lcol_csr.upload(lcol.data(), lcol.size(), c->stream));
+    HF_TRY(op.pp_lcol.alloc(op.padded_nnz, c->stream));
+    k_patch_lcol<<<(c->Npad + 255) / 256, 256, 0, c->stream>>>(c->N, c->Npad, R, c->rowptr.p, op.slice_ptr.p, lcol_csr.p, op.pp_lcol.p);
+    HF_CUDA(cudaGetLastError());
+    HF_TRY(op.pp_halo_ptr.upload(hptr.data(), hptr.size(), c->stream));
+    HF_TRY(op.pp_halo_idx.upload(hidx.data(), hidx.size(), c->stream));
+    HF_TRY(op.pp_pub.upload(pub.data(), pub.size(), c->stream));
+    op.pp_rpt = rpt;
+    op.pp_grid = G;
+    op.pp_mat_cap = mat_cap;
+    op.pp_halo_cap = halo_cap;
+    op.pp_smem = bytes;
+    HF_TRY(patch_set_smem_rpt(rpt, bytes));
+    PcgWork& w = c->ws;
+    if (w.acc.n == 0) {
+      HF_TRY(w.gen.alloc(1, c->stream));
+      HF_TRY(w.fail.alloc(1, c->stream));
+      HF_TRY(w.acc.alloc((size_t)2 * HF_NREP * HF_ACC_LINE, c->stream));
+      HF_TRY(w.acc_prev.alloc((size_t)2 * HF_NREP * HF_ACC_LINE, c->stream));
+    }
+    if (w.qpk.n < (size_t)2 * c->Npad) HF_TRY(w.qpk.alloc((size_t)2 * c->Npad, c->stream));
+    HF_CUDA(cudaStreamSynchronize(c->stream));           // lcol_csr goes out of scope
+    break;
+  }
+  return HF_OK;
+}
+
+int hf_patch_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts) {
+  PcgWork& w = c->ws;
+  if (!op.pp_rpt) return hf_fail(HF_ERR_STATE, "patch PCG kernel is not available for this mesh size");
+  PatchArgs a;
+  a.nslices = op.nslices;
+  a.slice_ptr = op.slice_ptr.p;
+  a.val = op.val.p;
+  a.lcol = op.pp_lcol.p;
+  a.halo_ptr = op.pp_halo_ptr.p;
+  a.halo_idx = op.pp_halo_idx.p;
+  a.pub = op.pp_pub.p;
+  a.x = w.x.p;
+  a.r = w.r.p;
+  a.qpk = w.qpk.p;
+  a.c = w.ctrl.p;
+  a.acc = w.acc.p;
+  a.acc_prev = w.acc_prev.p;
+  a.gen = w.gen.p;
+  a.iters_out = (step_slot >= 0 && (size_t)step_slot < w.step_iters.n) ? w.step_iters.p + step_slot : nullptr;
+  a.fail = w.fail.p;
+  a.max_it = c->max_iters;
+  a.npad = c->Npad;
+  a.nparts = sum_parts ? w.grid : 0;
+  a.rtol = c->rtol;
+  a.mat_cap = op.pp_mat_cap;
+  a.halo_cap = op.pp_halo_cap;
+  void* args[] = {&a};
+  const void* fn = nullptr;
+  switch (op.pp_rpt) {
+    case 4: fn = (const void*)k_pcg_patch<4>; break;
+    case 6: fn = (const void*)k_pcg_patch<6>; break;
+    case 8: fn = (const void*)k_pcg_patch<8>; break;
+    default: fn = (const void*)k_pcg_patch<10>; break;
+  }
+  HF_TRY(patch_set_smem_rpt(op.pp_rpt, op.pp_smem));   // per function, not per operator
+  HF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(op.pp_grid), dim3(HF_PT), args, op.pp_smem, c->stream));
+  c->stat_launches += 1;
+  return HF_OK;
+}

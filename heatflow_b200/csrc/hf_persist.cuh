@@ -1,0 +1,233 @@
+// heatflow_b200 - device helpers shared by the persistent PCG kernels (hf_persist.cu, hf_patch.cu):
+// flag-with-data packets, the ordered packet-tree reduction and the one-trip fixed-point reduction.
+#pragma once
+#include "hf_ctx.cuh"
+
+#ifndef HF_PT
+#define HF_PT 256       // threads per CTA (1 CTA/SM => up to 255 registers/thread for the cached operator rows)
+#endif
+#ifndef HF_SPW
+#define HF_SPW 4        // sliced-ELL slices per warp = rows per thread
+#endif
+#define HF_PW (HF_PT / 32)
+static_assert(HF_PT == HF_BLOCK, "hf_sum_parts / hf_block_sum stride over HF_BLOCK threads");
+#define HF_SLOT_STRIDE 8   // uint4 per slot: one 128-byte line each
+#define HF_MAX_GRID 160
+#define HF_RR_CHECK 64  // iterations between direct recomputations of ||r||^2
+#define HF_WR 8          // operator entries per row cached in registers
+
+__device__ __forceinline__ void hf_pkt_store(uint4* p, double v, unsigned gen) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(gen), "r"(hi), "r"(gen) : "memory");
+}
+__device__ __forceinline__ uint4 hf_pkt_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool hf_pkt_ok(const uint4& v, unsigned gen) { return v.y == gen && v.w == gen; }
+__device__ __forceinline__ double hf_pkt_val(const uint4& v) { return __hiloint2double((int)v.z, (int)v.x); }
+
+// Grid-wide sums of NV values per thread, split in two halves so that independent work can be
+// overlapped with the wait:  arrive = CTA reduction + publish,  wait = poll + broadcast.
+// Warp i (< NV) of every CTA handles value i.  CTA 0 is the reducer: it polls the other CTAs'
+// slots (all loads of a polling round in flight together), adds the partials in slot order and
+// broadcasts; the other CTAs poll the broadcast slot.  O(G) polling traffic per reduction.
+// Result: identical bits in every thread of every CTA.  No memory ordering is implied.
+template <int NV>
+__device__ __forceinline__ void hf_grid_arrive(const double (&v)[NV], uint4* slots, unsigned gen, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double t = hf_warp_sum(v[i]);
+    if (lane == 0) sh[warp * NV + i] = t;
+  }
+  __syncthreads();
+  if (warp < NV && blockIdx.x != 0) {
+    uint4* set = slots + (size_t)(gen & 1u) * (HF_MAX_GRID + 1) * HF_SLOT_STRIDE;
+    const double t = hf_warp_sum(lane < HF_PW ? sh[lane * NV + warp] : 0.0);
+    if (lane == 0) hf_pkt_store(set + (size_t)blockIdx.x * HF_SLOT_STRIDE + warp, t, gen);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void hf_grid_wait(double (&out)[NV], uint4* slots, int G, unsigned gen, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
+  uint4* set = slots + (size_t)(gen & 1u) * (HF_MAX_GRID + 1) * HF_SLOT_STRIDE;
+  uint4* bcast = set + (size_t)HF_MAX_GRID * HF_SLOT_STRIDE;
+  if (warp < NV) {
+    if (blockIdx.x != 0) {
+      if (lane == 0) {
+        uint4 s;
+        do {
+          s = hf_pkt_load(bcast + warp);
+        } while (!hf_pkt_ok(s, gen));
+        sh[HF_PW * NV + warp] = hf_pkt_val(s);
+      }
+    } else {
+      const double own = hf_warp_sum(lane < HF_PW ? sh[lane * NV + warp] : 0.0);
+      uint4 s[5];
+      bool need[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) need[k] = (lane + 32 * k) < G && (lane + 32 * k) > 0;
+      bool pending;
+      do {
+        pending = false;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          if (need[k]) s[k] = hf_pkt_load(set + (size_t)(lane + 32 * k) * HF_SLOT_STRIDE + warp);
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          if (need[k]) {
+            if (hf_pkt_ok(s[k], gen)) need[k] = false;
+            else pending = true;
+          }
+      } while (pending);
+      double acc = (lane == 0) ? own : 0.0;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int j = lane + 32 * k;
+        if (j > 0 && j < G) acc += hf_pkt_val(s[k]);
+      }
+      acc = hf_warp_sum(acc);
+      if (lane == 0) {
+        hf_pkt_store(bcast + warp, acc, gen);
+        sh[HF_PW * NV + warp] = acc;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) out[i] = sh[HF_PW * NV + i];
+}
+
+#ifndef HF_RED_MODE
+#define HF_RED_MODE 1    // 0: packet slots, CTA 0 reduces and broadcasts (two L2 trips); 1: fixed-point atomics (one trip)
+#endif
+#ifndef HF_NREP
+#define HF_NREP 8        // replicated accumulator lines (spreads the atomics of the G CTAs); <= 8 (4 polling lanes each)
+#endif
+#define HF_ACC_LINE 16   // 64-bit words per accumulator line (128 bytes)
+#define HF_FX_BITS 96    // a value below its bound 2^eb is accumulated as an integer multiple of 2^(eb - 96)
+#define HF_FX_MARGIN 12  // log2 of the safety factor on the magnitude estimates
+
+// ---- one-trip grid reduction with exact (order-independent) accumulation ------------------------------
+// Every CTA converts its partial sum t (|t| < 2^eb, eb known to all CTAs from shared scalars) to the
+// 96-bit fixed-point integer floor(t 2^(96-eb)) = hi 2^48 + lo and adds the two halves with 64-bit
+// integer atomics (RED, no return value) to one of HF_NREP accumulator lines.  Integer addition
+// commutes, so the total is independent of the arrival order: bit-reproducible like the ordered
+// packet tree, but with ONE store->load trip through L2 instead of two.  Each word carries its own
+// arrival count in its low 8 bits (every CTA adds (payload << 8) + 1), so a reader knows from the
+// word alone when all partials are in - no flag, fence or ordering between addresses is needed.
+// Words are never reset: readers work with the difference to the value the word had when the set was
+// last complete (kept in registers; carried from launch to launch through acc_prev).  Sets alternate
+// with the generation parity (a CTA can only add for generation g+2 after consuming g+1, which every
+// CTA contributes to only after consuming g).  A partial that is not finite or not below its bound
+// contributes a sentinel that turns the total into NaN in every CTA alike (the solve then fails loudly).
+struct FxState {
+  unsigned long long prev[2][2];   // [set][hi, lo] of this lane's chunk
+};
+
+__device__ __forceinline__ void hf_red_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void hf_ld2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// x < 2^hf_exp2(x) for a positive normal double (integer ops on the exponent field; 0, denormals and
+// non-finite values give out-of-range exponents, which end in the sentinel path / a harmless tiny scale)
+__device__ __forceinline__ int hf_exp2(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1022; }
+// t * 2^k without the software ldexp: two exact multiplications by powers of two (|k| <= 2000)
+__device__ __forceinline__ double hf_scale2(double t, int k) {
+  const int k1 = k / 2, k2 = k - k1;
+  return t * __hiloint2double((1023 + k1) << 20, 0) * __hiloint2double((1023 + k2) << 20, 0);
+}
+__device__ __forceinline__ int hf_clamp_exp(int e) { return max(-900, min(900, e)); }
+
+template <int NV>
+__device__ __forceinline__ void hf_fx_arrive(const double (&v)[NV], const int (&eb)[NV], unsigned long long* acc, unsigned gen,
+                                             double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double t = hf_warp_sum(v[i]);
+    if (lane == 0) sh[warp * NV + i] = t;
+  }
+  __syncthreads();
+  if (warp < NV) {
+    const double t = hf_warp_sum(lane < HF_PW ? sh[lane * NV + warp] : 0.0);
+    if (lane == 0) {
+      int e = eb[0];
+#pragma unroll
+      for (int i = 1; i < NV; ++i)
+        if (warp == i) e = eb[i];
+      const double x = hf_scale2(t, 48 - e);              // |x| < 2^48 when |t| < 2^e
+      long long hi;
+      unsigned long long lo;
+      if (fabs(x) < 281474976710656.0) {                  // 2^48; false for NaN / Inf as well
+        const double f = floor(x);
+        hi = (long long)f;
+        lo = (unsigned long long)((x - f) * 281474976710656.0);
+      } else {
+        hi = 1ll << 54;                                   // sentinel: the total decodes to NaN in every CTA
+        lo = 0ull;
+      }
+      unsigned long long* line = acc + ((size_t)(gen & 1u) * HF_NREP + (blockIdx.x % HF_NREP)) * HF_ACC_LINE + 2 * warp;
+      hf_red_add(line, ((unsigned long long)hi << 8) + 1ull);
+      hf_red_add(line + 1, (lo << 8) + 1ull);
+    }
+  }
+}
+
+// Warp 0 polls: lane l reads the 16-byte chunk (value l & 3, replica l >> 2).
+template <int NV>
+__device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV], const unsigned long long* acc, int G, unsigned gen,
+                                           double* red, FxState& st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
+  if (warp == 0) {
+    const int set = (int)(gen & 1u);
+    const int i = lane & 3, r = lane >> 2;
+    const int members = (r < G && r < HF_NREP) ? (G - 1 - r) / HF_NREP + 1 : 0;
+    const bool active = i < NV && members > 0;
+    const unsigned long long* chunk = acc + ((size_t)set * HF_NREP + r) * HF_ACC_LINE + 2 * i;
+    unsigned long long whi = 0ull, wlo = 0ull;
+    bool ok = !active;
+    for (;;) {
+      if (!ok) {
+        hf_ld2(chunk, whi, wlo);
+        ok = ((whi - st.prev[set][0]) & 0xffull) == (unsigned long long)members &&
+             ((wlo - st.prev[set][1]) & 0xffull) == (unsigned long long)members;
+      }
+      if (__all_sync(0xffffffffu, ok)) break;
+    }
+    long long shi = 0;
+    unsigned long long slo = 0ull;
+    if (active) {
+      shi = (long long)(whi - st.prev[set][0] - (unsigned long long)members) >> 8;
+      slo = (wlo - st.prev[set][1] - (unsigned long long)members) >> 8;
+      st.prev[set][0] = whi;
+      st.prev[set][1] = wlo;
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {                    // over the replicas: exact integer sums
+      shi += __shfl_xor_sync(0xffffffffu, shi, o);
+      slo += __shfl_xor_sync(0xffffffffu, slo, o);
+    }
+    if (lane < NV) {
+      int e = eb[0];
+#pragma unroll
+      for (int k = 1; k < NV; ++k)
+        if (lane == k) e = eb[k];
+      const bool bad = shi >= (1ll << 53) || shi <= -(1ll << 53);
+      const double val = hf_scale2(fma((double)shi, 281474976710656.0, (double)slo), e - HF_FX_BITS);
+      sh[HF_PW * NV + lane] = bad ? __longlong_as_double(0x7ff8000000000000ll) : val;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) out[i] = sh[HF_PW * NV + i];
+}

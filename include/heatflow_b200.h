@@ -88,8 +88,9 @@ int hf_get_state(hf_ctx* ctx, double* u);
 int hf_set_source(hf_ctx* ctx, const double* s);
 
 /* solver options: rtol on ||r||_{D^-1} / ||b_free||_{D^-1}, iteration cap, warm start
- * (x0 = u_n + warm*(u_n - u_{n-1})), PCG kernels: 0 = auto, 1 = streaming 2-kernel/iteration
- * graph, 2 = persistent cooperative kernel. */
+ * (x0 = u_n + warm*(u_n - u_{n-1})), PCG kernels: 0 = auto (on-chip when the mesh fits, else
+ * streaming), 1 = streaming kernel (one launch per iteration), 2 = on-chip persistent kernel
+ * (contiguous-range variant when it fits, else the patch variant), 3 = patch variant. */
 int hf_set_solver(hf_ctx* ctx, double rtol, int32_t max_iters, double warm, int32_t mode);
 
 /* Initial guess from the previous time steps: keep the corrections of up to max_vectors

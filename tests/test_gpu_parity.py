@@ -14,6 +14,8 @@ from oracle import heat_oracle as ho
 pytestmark = pytest.mark.gpu
 
 RTOL_FIELD = 1e-10   # the tolerance north_star states for temperature histories
+# node ordering per solver mode: the patch kernel (mode 3) is meant for Hilbert-ordered meshes
+ORDERING = {0: "auto", 1: "auto", 2: "auto", 3: "hilbert"}
 
 
 def rel_err(a, b):
@@ -88,11 +90,11 @@ def test_rhs_and_single_step(small_nd):
     s.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["streaming", "persistent", "patch"])
 @pytest.mark.parametrize("name", ["geballe_no_diamond", "geballe_with_diamond"])
 def test_history_every_step(name, mode):
     c = build_case(name, 8.0)
-    s = make_solver(c, mode=mode)
+    s = make_solver(c, mode=mode, ordering=ORDERING[mode])
     O = make_oracle(c)
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.9e-6, 0.0)])
     hist, iters, fields = s.run(c.amps, c.ic, c.coeff, watch, keep_fields=True)
@@ -149,11 +151,11 @@ def test_constant_state_invariance(small_wd):
     s.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["streaming", "persistent", "patch"])
 def test_full_size_no_diamond_vs_oracle(mode):
     # configs[1] at the cfg's own mesh sizes (~1.1e5 dofs, 40 steps)
     c = build_case("geballe_no_diamond", 1.0)
-    s = make_solver(c, mode=mode)
+    s = make_solver(c, mode=mode, ordering=ORDERING[mode])
     O = make_oracle(c)
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
     hist, iters, _ = s.run(c.amps, c.ic, c.coeff, watch)
@@ -163,12 +165,12 @@ def test_full_size_no_diamond_vs_oracle(mode):
     s.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["streaming", "persistent", "patch"])
 def test_run_is_bit_reproducible(small_nd, mode):
     c = small_nd
     out = []
     for _ in range(2):
-        s = make_solver(c, mode=mode)
+        s = make_solver(c, mode=mode, ordering=ORDERING[mode])
         hist, iters, _ = s.run(c.amps[:25], c.ic, c.coeff, [5, 50])
         out.append((hist, iters, s.get_state()))
         s.close()
@@ -177,11 +179,11 @@ def test_run_is_bit_reproducible(small_nd, mode):
     assert np.array_equal(out[0][2], out[1][2])
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["streaming", "persistent", "patch"])
 def test_warm_start_default_of_the_runners_vs_oracle(mode):
     # the runners start every solve from u_n + (u_n - u_{n-1}); same 1e-10 bar against the LU oracle
     c = build_case("geballe_with_diamond", 4.0)
-    s = make_solver(c, warm=1.0, mode=mode)
+    s = make_solver(c, warm=1.0, mode=mode, ordering=ORDERING[mode])
     O = make_oracle(c)
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
     hist, iters, fields = s.run(c.amps, c.ic, c.coeff, watch, keep_fields=True)
@@ -238,11 +240,11 @@ def test_error_paths(small_nd):
 
 
 # ---- initial guess recycled from the previous solves (hf_set_recycle, the runners' default) ----
-@pytest.mark.parametrize("mode", [1, 2], ids=["streaming", "persistent"])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["streaming", "persistent", "patch"])
 @pytest.mark.parametrize("cap", [128, 6], ids=["full-history", "frozen-when-full"])
 def test_recycled_initial_guess_vs_oracle_every_step(mode, cap):
     c = build_case("geballe_with_diamond", 4.0)
-    s = make_solver(c, warm=1.0, mode=mode, recycle=cap)
+    s = make_solver(c, warm=1.0, mode=mode, recycle=cap, ordering=ORDERING[mode])
     O = make_oracle(c)
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
     hist, iters, fields = s.run(c.amps, c.ic, c.coeff, watch, keep_fields=True)
@@ -289,3 +291,22 @@ def test_recycle_single_steps_and_argument_errors(small_nd):
     assert rel_err(s.get_state(), s2.get_state()) <= 1e-11
     s.close()
     s2.close()
+
+
+def test_mid_size_mesh_runs_on_chip_with_the_patch_kernel():
+    # 2.2e5 dofs (the size of the reference's own gmsh meshes): too large for the contiguous-range kernel,
+    # auto mode picks the Hilbert order and the patch kernel; runner defaults (warm start + recycled guess)
+    c = build_case("geballe_with_diamond", 0.8)
+    s = make_solver(c, warm=1.0, recycle=32)
+    assert s.on_chip()
+    O = make_oracle(c)
+    watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
+    S = 16
+    hist, iters, _ = s.run(c.amps[:S], c.ic, c.coeff, watch)
+    ohist, _ = O.run(S, watch)
+    assert np.abs(hist / ohist - 1).max() <= RTOL_FIELD
+    assert rel_err(s.get_state(), O.u) <= RTOL_FIELD
+    l0 = s.stats()["launches"]
+    s.run(c.amps[S:S + 2], c.ic, c.coeff, watch)
+    assert s.stats()["launches"] - l0 < 40              # one solver launch per step, not one per iteration
+    s.close()
