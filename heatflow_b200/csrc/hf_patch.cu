@@ -7,7 +7,8 @@
 // (~4 sqrt(R) rows instead of two full mesh rows), so per row the CTA keeps
 //   operator   8 B value + 2 B local column per stored entry       (~85 B, sliced-ELL padding included)
 //   vectors    r, p on own + halo rows, q on halo rows              (~18 B)
-// in shared memory and x in registers: up to R = 2560 rows per SM, 148 x 2560 = 3.8e5 dofs on chip.
+// on chip: x and the first K entries of every row in registers (the 256 KB register file is otherwise idle),
+// the remaining entries and the vectors in shared memory - up to R = 3584 rows per SM.
 // The streaming kernel (hf_pcg.cu) needs ~17-21 us per iteration at these sizes (L2-resident, bound
 // by launch and chunk latency); this kernel needs ~4-6 us.
 // Only rows that appear in another CTA's halo list publish their q packet.
@@ -39,9 +40,10 @@ struct PatchArgs {
   int mat_cap, halo_cap;
 };
 
-template <int RPT>
+template <int RPT, int K>
 __global__ void __launch_bounds__(HF_PT, 1) k_pcg_patch(PatchArgs P) {
   constexpr int R = HF_PT * RPT;
+  constexpr int NSL = R / 32;                    // slices per chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sval = reinterpret_cast<double*>(smem_raw);
   double* sp = sval + P.mat_cap;                 // p: own rows [0, R), halo [R, R + nh)
@@ -49,18 +51,39 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_patch(PatchArgs P) {
   double* sqh = sr + R + P.halo_cap;             // validated halo q values
   double* red = sqh + P.halo_cap;                // reduction scratch: 2 x (HF_PW*3 + 3)
   int* shal = reinterpret_cast<int*>(red + 2 * (HF_PW * 3 + 3) + 2);   // halo rows (global indices)
-  unsigned short* scol = reinterpret_cast<unsigned short*>(shal + P.halo_cap);
+  int* sbase = shal + P.halo_cap;                // [NSL + 1] offsets of the slices' shared-memory parts
+  unsigned short* scol = reinterpret_cast<unsigned short*>(sbase + ((NSL + 4) & ~3));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, nsl = P.nslices;
   const int f = blockIdx.x * (R / 32);
   const int fend = min(f + R / 32, nsl);
-  const int e0 = P.slice_ptr[min(f, nsl)], e1 = P.slice_ptr[fend];
   const int lo = blockIdx.x * R;
   const int hp = P.halo_ptr[blockIdx.x];
   const int nh = P.halo_ptr[blockIdx.x + 1] - hp;
-  for (int i = tid; i < e1 - e0; i += HF_PT) {
-    sval[i] = P.val[e0 + i];
-    scol[i] = P.lcol[e0 + i];
+  // shared-memory offsets of the slices: entries K.. of every row (the first K live in registers)
+  if (warp == 0) {
+    constexpr int PER = (NSL + 31) / 32;
+    int cnt[PER], tot = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int sl = lane * PER + j, s = f + sl;
+      cnt[j] = (sl < NSL && s < nsl) ? max(((P.slice_ptr[s + 1] - P.slice_ptr[s]) >> 5) - K, 0) * 32 : 0;
+      tot += cnt[j];
+    }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int run = incl - tot;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int sl = lane * PER + j;
+      if (sl <= NSL) sbase[sl] = run;
+      run += cnt[j];
+    }
+    if (lane == 31 && PER * 32 == NSL) sbase[NSL] = run;
   }
   for (int i = tid; i < R; i += HF_PT) {
     const double rv = (lo + i < P.npad) ? P.r[lo + i] : 0.0;
@@ -74,21 +97,40 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_patch(PatchArgs P) {
     sr[R + h] = rv;
     sp[R + h] = rv;
   }
+  __syncthreads();                               // sbase
   int base[RPT], wid[RPT];
   double x[RPT], q[RPT];
+  double mv[RPT][K > 0 ? K : 1];
+  int mc[RPT][K > 0 ? K : 1];
   unsigned pubmask = 0u;
 #pragma unroll
   for (int k = 0; k < RPT; ++k) {
-    const int s = f + warp * RPT + k;
+    const int sl = warp * RPT + k, s = f + sl;
     base[k] = 0;
     wid[k] = -1;                                 // marks "no slice"
     x[k] = q[k] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) {
+      mv[k][kk] = 0.0;
+      mc[k][kk] = sl * 32 + lane;
+    }
     if (s < nsl) {
       const int b0 = P.slice_ptr[s];
-      base[k] = b0 - e0 + lane;
-      wid[k] = (P.slice_ptr[s + 1] - b0) >> 5;
+      const int w = (P.slice_ptr[s + 1] - b0) >> 5;
+      wid[k] = w;
+      base[k] = sbase[sl] + lane;
       x[k] = P.x[s * 32 + lane];
       if (P.pub[s * 32 + lane]) pubmask |= 1u << k;
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk)
+        if (kk < w) {
+          mv[k][kk] = P.val[b0 + kk * 32 + lane];
+          mc[k][kk] = P.lcol[b0 + kk * 32 + lane];
+        }
+      for (int kk = K; kk < w; ++kk) {           // the warp's own slices: coalesced
+        sval[base[k] + (kk - K) * 32] = P.val[b0 + kk * 32 + lane];
+        scol[base[k] + (kk - K) * 32] = P.lcol[b0 + kk * 32 + lane];
+      }
     }
   }
   double thr, rr;                                // stopping threshold and ||r_0||^2
@@ -130,8 +172,13 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_patch(PatchArgs P) {
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       if (wid[k] >= 0) {
-        const int w = wid[k], b = base[k];
+        const int w = wid[k] - K, b = base[k];    // entries beyond the register-cached ones
         double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+          if (kk & 1) a1 = fma(mv[k][kk], sp[mc[k][kk]], a1);
+          else a0 = fma(mv[k][kk], sp[mc[k][kk]], a0);
+        }
         int kk = 0;
         for (; kk + 2 <= w; kk += 2) {
           const int c0 = scol[b + kk * 32], c1 = scol[b + (kk + 1) * 32];
@@ -275,21 +322,27 @@ __global__ void k_patch_lcol(int N, int Npad, int R, const int* __restrict__ row
 
 static size_t patch_smem_bytes(int R, int mat_cap, int halo_cap) {
   return sizeof(double) * ((size_t)mat_cap + 2 * ((size_t)R + halo_cap) + halo_cap + 2 * (HF_PW * 3 + 3) + 2) +
-         sizeof(int) * (size_t)halo_cap + sizeof(unsigned short) * (size_t)mat_cap;
+         sizeof(int) * ((size_t)halo_cap + ((R / 32 + 4) & ~3)) + sizeof(unsigned short) * (size_t)mat_cap;
 }
 
-template <int RPT>
-static int patch_set_smem(size_t bytes) {
-  HF_CUDA(cudaFuncSetAttribute(k_pcg_patch<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return HF_OK;
+// (rows per thread, register-cached entries per row): the cache is sized to the register budget of one
+// CTA of 256 threads per SM (255 registers per thread)
+static const int kPatchRpt[6] = {4, 6, 8, 10, 12, 14};
+static const int kPatchK[6] = {8, 6, 4, 4, 3, 2};
+
+static const void* patch_kernel(int rpt) {
+  switch (rpt) {
+    case 4: return (const void*)k_pcg_patch<4, 8>;
+    case 6: return (const void*)k_pcg_patch<6, 6>;
+    case 8: return (const void*)k_pcg_patch<8, 4>;
+    case 10: return (const void*)k_pcg_patch<10, 4>;
+    case 12: return (const void*)k_pcg_patch<12, 3>;
+    default: return (const void*)k_pcg_patch<14, 2>;
+  }
 }
 static int patch_set_smem_rpt(int rpt, size_t bytes) {
-  switch (rpt) {
-    case 4: return patch_set_smem<4>(bytes);
-    case 6: return patch_set_smem<6>(bytes);
-    case 8: return patch_set_smem<8>(bytes);
-    default: return patch_set_smem<10>(bytes);
-  }
+  HF_CUDA(cudaFuncSetAttribute(patch_kernel(rpt), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return HF_OK;
 }
 
 // Decide rows per thread / grid / shared-memory layout; pp_rpt = 0 when the mesh does not fit.
@@ -304,15 +357,16 @@ int hf_patch_plan(hf_ctx* c, SellOp& op) {
   std::vector<int> sp(nsl + 1);
   HF_CUDA(cudaMemcpyAsync(sp.data(), op.slice_ptr.p, sizeof(int) * (nsl + 1), cudaMemcpyDeviceToHost, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
-  static const int kRpt[4] = {4, 6, 8, 10};
-  for (int t = 0; t < 4; ++t) {
-    const int rpt = kRpt[t], R = HF_PT * rpt;
+  for (int t = 0; t < 6; ++t) {
+    const int rpt = kPatchRpt[t], K = kPatchK[t], R = HF_PT * rpt;
     const int G = (c->Npad + R - 1) / R;
     if (G > c->sm_count || G > HF_MAX_GRID) continue;
-    int mat_cap = 0;
+    int mat_cap = 0;                              // shared-memory part of a chunk's operator: entries K.. of every row
     for (int b = 0; b < G; ++b) {
       const int f = std::min(b * (R / 32), nsl), fe = std::min(f + R / 32, nsl);
-      mat_cap = std::max(mat_cap, sp[fe] - sp[f]);
+      int n = 0;
+      for (int sl = f; sl < fe; ++sl) n += std::max(((sp[sl + 1] - sp[sl]) >> 5) - K, 0) * 32;
+      mat_cap = std::max(mat_cap, n);
     }
     std::vector<int> hptr, hidx;
     std::vector<unsigned short> lcol;
@@ -382,13 +436,7 @@ int hf_patch_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_pa
   a.mat_cap = op.pp_mat_cap;
   a.halo_cap = op.pp_halo_cap;
   void* args[] = {&a};
-  const void* fn = nullptr;
-  switch (op.pp_rpt) {
-    case 4: fn = (const void*)k_pcg_patch<4>; break;
-    case 6: fn = (const void*)k_pcg_patch<6>; break;
-    case 8: fn = (const void*)k_pcg_patch<8>; break;
-    default: fn = (const void*)k_pcg_patch<10>; break;
-  }
+  const void* fn = patch_kernel(op.pp_rpt);
   HF_TRY(patch_set_smem_rpt(op.pp_rpt, op.pp_smem));   // per function, not per operator
   HF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(op.pp_grid), dim3(HF_PT), args, op.pp_smem, c->stream));
   c->stat_launches += 1;

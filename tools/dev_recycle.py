@@ -16,7 +16,7 @@ def probe(name, scale, steps, caps, mode=0, check=True):
         O = make_oracle(c)
         _, ofields = O.run(steps, [0], keep_fields=True)
     for cap in caps:
-        s = make_solver(c, warm=1.0, mode=mode)
+        s = make_solver(c, warm=1.0, mode=mode, ordering=os.environ.get("HF_ORD", "auto"))
         n, nnz = s.sizes()
         s.set_recycle(cap)
         s.run(c.amps[20:23], c.ic, c.coeff, [0])
