@@ -222,13 +222,15 @@ def large_mesh_run(case, device, rtol, warm, recycle):
     """BASELINE config #4: the whole konopkova run on the >= 1 M-dof mesh with the runner defaults."""
     s = configured_solver(case, device, rtol, warm=warm, recycle=recycle)
     n, nnz = s.sizes()
+    path_id = s.solver_path()
     s.set_state(np.full(n, case.ic))
     s.run(case.amps[:2], case.ic, case.coeff, [0])                      # warm-up: graphs captured
     s.set_state(np.full(n, case.ic))
     _, iters, _ = s.run(case.amps, case.ic, case.coeff, [0])
     ms = s.stats()["run_ms"]
     s.close()
-    return {"workload": f"konopkova refined, N={n} dofs, nnz={nnz}, {case.num_steps} steps, streaming kernel, "
+    path = {1: "streaming kernel", 2: "on-chip contiguous-range kernel", 3: "on-chip patch kernel"}[path_id]
+    return {"workload": f"{case.name} refined, N={n} dofs, nnz={nnz}, {case.num_steps} steps, {path}, "
                         f"recycled initial guess {recycle} vectors", "value": n * case.num_steps / (ms * 1e-3),
             "unit": "DOF-timesteps/s", "ms_per_step": ms / case.num_steps, "pcg_iterations_total": int(iters.sum())}
 
@@ -288,7 +290,8 @@ def run_ours(args, rank, world, local_rank):
     solve_ms, solve_launches = s.solve_profile()
     prof_run_ms = s.stats()["run_ms"]
     s.set_profile(False)
-    persistent = s.on_chip()                              # one cooperative k_pcg_persist launch per solve
+    persistent = s.on_chip()                              # one cooperative launch per solve
+    persist_kernel = {2: "k_pcg_persist", 3: "k_pcg_patch"}.get(s.solver_path(), "k_pcg_iter")
 
     # ---- sweep tile: 16 (k, fwhm) variants of config #5 per GPU through the sweep engine's path for this mesh
     # (heatflow_b200/sweep.py: 'serial' when the mesh fits on chip, else the batched ensemble kernels);
@@ -356,17 +359,17 @@ def run_ours(args, rank, world, local_rank):
         pass
     share = solve_ms / prof_run_ms if prof_run_ms > 0 else None
     if persistent:
-        alg = iter_bytes(n, nnz) * float(iters_p.sum()) / steps        # per k_pcg_persist launch (= per time step)
+        alg = iter_bytes(n, nnz) * float(iters_p.sum()) / steps        # per solver launch (= per time step)
         us = solve_ms * 1e3 / steps
-        roof = {"bound": "hbm", "kernel": "k_pcg_persist", "achieved": alg / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
-                "traffic": traffic.get("k_pcg_persist"), "algorithmic_bytes_per_launch": alg, "launch_us": us,
+        roof = {"bound": "hbm", "kernel": persist_kernel, "achieved": alg / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                "traffic": traffic.get(persist_kernel), "algorithmic_bytes_per_launch": alg, "launch_us": us,
                 "pcg_iterations_per_launch": float(iters_p.sum()) / steps, "share_of_step_time": share,
                 "peak_source": peak_src,
-                "note": "operator and vectors live in shared memory / registers for the whole solve, so the kernel is bound by "
+                "note": "operator and vectors live in registers / shared memory for the whole solve, so the kernel is bound by "
                         "the latency of its one grid reduction per PCG iteration, not by HBM; achieved is the HBM-EQUIVALENT "
                         "rate: the bytes a streaming PCG iteration moves (10 nnz + 64 N) x iterations / launch time (its real "
                         "DRAM traffic is in `traffic`); the HBM-bound kernel of this code base is k_pcg_iter, see roofline_1m",
-                "how": "CUDA events on the solver stream around every k_pcg_persist launch of a separate pass over the same "
+                "how": "CUDA events on the solver stream around every solver launch of a separate pass over the same "
                        "steps (hf_set_profile), summed / launches"}
     else:
         alg = iter_bytes(n, nnz)
@@ -406,6 +409,8 @@ def run_ours(args, rank, world, local_rank):
         line["roofline_1m"] = streaming_roofline(cl, local_rank, args.rtol, peak, peak_src, steps=3,
                                                  traffic=traffic.get("k_pcg_iter_1m"))
         line["konopkova_1m"] = large_mesh_run(cl, local_rank, args.rtol, args.warm_start, min(args.recycle, 64))
+        # the size of the reference's own gmsh meshes (2.1e5 - 4.3e5 nodes): still on chip
+        line["mid_mesh"] = large_mesh_run(build_case(WORKLOAD, 0.6), local_rank, args.rtol, args.warm_start, args.recycle)
     # CPU baseline on this host (bounded sample)
     if not args.skip_cpu:
         cb_steps = min(20, steps)

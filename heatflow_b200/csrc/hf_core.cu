@@ -154,11 +154,12 @@ extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const do
   c->nv = nv;
   c->Npad = (N + HF_SLICE - 1) / HF_SLICE * HF_SLICE;
   c->op_built = c->proj_built = false;
-  // ---- internal numbering.  auto: meshes small enough for the on-chip persistent kernel keep the
-  // caller's (banded) order, which that kernel's contiguous ghost ranges rely on; larger meshes are
-  // sorted along a Hilbert curve so that consecutive rows form compact 2-D patches.
+  // ---- internal numbering.  auto: triangle meshes are sorted along a Hilbert curve so that consecutive
+  // rows form compact 2-D patches with short halo lists (patch kernel, streaming kernel, ensembles); the
+  // caller's (banded) order is kept on request (hf_set_ordering(ctx, 1): contiguous-range kernel) and for
+  // 1-D meshes.
   int ordering = c->ordering_req;
-  if (ordering == 0) ordering = (nv == 3 && c->Npad > c->sm_count * 1024) ? 2 : 1;
+  if (ordering == 0) ordering = (nv == 3) ? 2 : 1;
   if (nv != 3) ordering = 1;
   c->permuted = (ordering == 2);
   c->h_rank.clear();
@@ -611,8 +612,8 @@ extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
   HF_TRY(cell_coefs(c, 1.0, dt));
   HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valA0.p));
   HF_TRY(hf_build_sell(c, c->valA0, true, c->opA, &c->valA));
-  HF_TRY(hf_persist_plan(c, c->opA));
-  if (!c->opA.p_spw) HF_TRY(hf_patch_plan(c, c->opA));
+  HF_TRY(hf_patch_plan(c, c->opA));
+  if (!c->opA.pp_rpt) HF_TRY(hf_persist_plan(c, c->opA));
   c->valM1.release();
   c->op_built = true;
   c->proj_built = false;
@@ -819,17 +820,18 @@ __global__ void k_sample(int n, const int* __restrict__ nodes, const double* __r
 
 // 0 = streaming graph chunks (host polls), 1 = persistent single-launch kernel
 static int pick_persist(hf_ctx* c, const SellOp& op, bool* persist) {
-  if (c->mode == 3 && !op.pp_rpt) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));   // forced: plan on demand
-  const bool fits = op.p_spw != 0 || op.pp_rpt != 0;     // contiguous-range kernel or patch kernel
-  if ((c->mode == 2 && !fits) || (c->mode == 3 && !op.pp_rpt))
+  // a specific on-chip kernel was requested: plan it on demand
+  if (c->mode == 3 && !op.pp_rpt) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));
+  if (c->mode == 2 && !op.p_spw) HF_TRY(hf_persist_plan(c, const_cast<SellOp&>(op)));
+  if ((c->mode == 2 && !op.p_spw) || (c->mode == 3 && !op.pp_rpt))
     return hf_fail(HF_ERR_STATE, "an on-chip PCG kernel was requested (solver mode 2 / 3) but the mesh does not fit on chip");
-  *persist = (c->mode >= 2) || (c->mode == 0 && fits);
+  *persist = (c->mode >= 2) || (c->mode == 0 && (op.pp_rpt != 0 || op.p_spw != 0));
   return HF_OK;
 }
 
-// one cooperative launch per solve: the contiguous-range kernel when its plan exists, else the patch kernel
+// one cooperative launch per solve: auto prefers the patch kernel (faster at every size it fits)
 static int solve_on_chip(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts) {
-  if (op.p_spw && c->mode != 3) return hf_pcg_solve_async(c, op, step_slot, sum_parts);
+  if (c->mode == 2 || !op.pp_rpt) return hf_pcg_solve_async(c, op, step_slot, sum_parts);
   return hf_patch_solve_async(c, op, step_slot, sum_parts);
 }
 
@@ -990,7 +992,8 @@ extern "C" int hf_get_solver_path(hf_ctx* c) {
   if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_get_solver_path: operator not built");
   bool persist = false;
   HF_TRY(pick_persist(c, c->opA, &persist));
-  return persist ? 2 : 1;
+  if (!persist) return 1;
+  return (c->mode == 2 || !c->opA.pp_rpt) ? 2 : 3;
 }
 
 extern "C" int hf_get_stats(hf_ctx* c, double* st) {
@@ -1113,8 +1116,8 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 0.0, c->ck.p);
     HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, 1, vals.p));
     HF_TRY(hf_build_sell(c, vals, false, c->opMr, nullptr));
-    HF_TRY(hf_persist_plan(c, c->opMr));
-    if (!c->opMr.p_spw) HF_TRY(hf_patch_plan(c, c->opMr));
+    HF_TRY(hf_patch_plan(c, c->opMr));
+    if (!c->opMr.pp_rpt) HF_TRY(hf_persist_plan(c, c->opMr));
     HF_TRY(c->proj_b.alloc((size_t)2 * c->Npad, c->stream));
     HF_TRY(c->proj_g.alloc((size_t)2 * c->N, c->stream));
     c->proj_built = true;

@@ -106,12 +106,16 @@ class HeatSolver:
         earlier solves of this simulation (dropped by ``set_state`` / ``build_operator``)."""
         _lib.check(self._L.hf_set_recycle(self._h, int(max_vectors)))
 
-    def on_chip(self):
-        """True when the time loop runs in the persistent on-chip PCG kernel (hf_get_solver_path)."""
+    def solver_path(self):
+        """1 = streaming kernel, 2 = on-chip contiguous-range kernel, 3 = on-chip patch kernel."""
         rc = self._L.hf_get_solver_path(self._h)
         if rc < 0:
             _lib.check(rc)
-        return rc == 2
+        return rc
+
+    def on_chip(self):
+        """True when the time loop runs in a persistent on-chip PCG kernel (one launch per solve)."""
+        return self.solver_path() >= 2
 
     def sizes(self):
         n, nnz = C.c_int32(), C.c_int64()

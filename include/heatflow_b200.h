@@ -88,9 +88,9 @@ int hf_get_state(hf_ctx* ctx, double* u);
 int hf_set_source(hf_ctx* ctx, const double* s);
 
 /* solver options: rtol on ||r||_{D^-1} / ||b_free||_{D^-1}, iteration cap, warm start
- * (x0 = u_n + warm*(u_n - u_{n-1})), PCG kernels: 0 = auto (on-chip when the mesh fits, else
- * streaming), 1 = streaming kernel (one launch per iteration), 2 = on-chip persistent kernel
- * (contiguous-range variant when it fits, else the patch variant), 3 = patch variant. */
+ * (x0 = u_n + warm*(u_n - u_{n-1})), PCG kernels: 0 = auto (on-chip patch kernel when the mesh
+ * fits, else streaming), 1 = streaming kernel (one launch per iteration), 2 = on-chip kernel with
+ * contiguous ghost ranges (banded node order, <= 1.5e5 dofs), 3 = on-chip patch kernel. */
 int hf_set_solver(hf_ctx* ctx, double rtol, int32_t max_iters, double warm, int32_t mode);
 
 /* Initial guess from the previous time steps: keep the corrections of up to max_vectors
@@ -132,8 +132,8 @@ int hf_set_profile(hf_ctx* ctx, int32_t on);
 int hf_get_solve_profile(hf_ctx* ctx, double* solve_ms, int64_t* solve_launches);
 
 /* Which PCG kernel hf_step / hf_run will use for the current operator and hf_set_solver mode:
- * 2 = persistent on-chip kernel (the mesh fits in the SMs' shared memory), 1 = streaming kernel;
- * < 0 on error. */
+ * 1 = streaming kernel, 2 = on-chip kernel with contiguous ghost ranges, 3 = on-chip patch kernel
+ * (the mesh fits in the SMs' shared memory + registers); < 0 on error. */
 int hf_get_solver_path(hf_ctx* ctx);
 
 /* Counters for benchmarking: stats[0] = device time of the step loop of the last hf_run /

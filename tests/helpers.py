@@ -40,6 +40,7 @@ def build_case(cfg_name="geballe_no_diamond", size_scale=8.0, growth=1.3):
     with contextlib.redirect_stdout(io.StringIO()):
         arrays = mesh.build_mesh()
     c = Case()
+    c.name = cfg_name
     c.cfg, c.mats, c.bounds, c.arrays = cfg, mats, bounds, arrays
     c.nodes, c.tris, c.cell_tag = arrays.nodes, arrays.tris, arrays.cell_tag
     c.tags = np.array([m.tag for m in mats], dtype=np.int32)
