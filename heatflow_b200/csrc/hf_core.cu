@@ -154,6 +154,8 @@ extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const do
   c->nv = nv;
   c->Npad = (N + HF_SLICE - 1) / HF_SLICE * HF_SLICE;
   c->op_built = c->proj_built = false;
+  c->opA.struct_valid = c->opMr.struct_valid = false;
+  c->opA.pp_rpt = c->opA.p_spw = c->opMr.pp_rpt = c->opMr.p_spw = 0;
   // ---- internal numbering.  auto: triangle meshes are sorted along a Hilbert curve so that consecutive
   // rows form compact 2-D patches with short halo lists (patch kernel, streaming kernel, ensembles); the
   // caller's (banded) order is kept on request (hf_set_ordering(ctx, 1): contiguous-range kernel) and for
@@ -509,7 +511,28 @@ int hf_build_patches(const hf_ctx* c, int R, std::vector<int>& halo_ptr, std::ve
   return HF_OK;
 }
 
+// values of an operator whose structure (slices, patches, local columns, plans) is already on the device
+static int sell_fill_values(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out) {
+  if (val_bc_out && val_bc_out->n != (size_t)c->nnz) HF_TRY(val_bc_out->alloc(c->nnz, c->stream));
+  DevBuf<int> bad;
+  HF_TRY(bad.alloc(1, c->stream));
+  const int g = (c->Npad + 255) / 256;
+  k_diag_scale<<<g, 256, 0, c->stream>>>(c->N, c->Npad, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
+                                         op.scale.p, bad.p);
+  k_fill_sell<<<g, 256, 0, c->stream>>>(c->N, c->Npad, op.R, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
+                                        op.scale.p, op.slice_ptr.p, op.lcol_csr.p, op.col.p, op.lcol.p, op.val.p,
+                                        val_bc_out ? val_bc_out->p : nullptr);
+  HF_CUDA(cudaGetLastError());
+  int hbad = 0;
+  HF_TRY(bad.download(&hbad, 1, c->stream));
+  if (hbad) return hf_fail(HF_ERR_STATE, "operator has a non-positive diagonal at row " + std::to_string(hbad - 1) +
+                                             " (unset material or degenerate cell?)");
+  return HF_OK;
+}
+
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out) {
+  // sweeps re-assemble with other material values on the same mesh: the structure is kept, only values move
+  if (op.struct_valid) return sell_fill_values(c, csr_val, apply_bc, op, val_bc_out);
   const int nsl = c->Npad / HF_SLICE;
   std::vector<int> sp(nsl + 1, 0);
   for (int s = 0; s < nsl; ++s) {
@@ -552,8 +575,7 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
                                        " rows); use hf_set_ordering(ctx, 2)");
     op.iter_smem = op.stage_bytes * op.nstages;
   }
-  DevBuf<unsigned short> lcol_csr;
-  HF_TRY(lcol_csr.upload(lcol.data(), lcol.size(), c->stream));
+  HF_TRY(op.lcol_csr.upload(lcol.data(), lcol.size(), c->stream));
   HF_TRY(op.halo_ptr.upload(hptr.data(), hptr.size(), c->stream));
   if (hidx.empty()) hidx.push_back(0);
   HF_TRY(op.halo_idx.upload(hidx.data(), hidx.size(), c->stream));
@@ -564,21 +586,9 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   HF_TRY(op.lcol.alloc(op.padded_nnz, c->stream));
   HF_TRY(op.val.alloc(op.padded_nnz, c->stream));
   HF_TRY(op.scale.alloc(c->Npad, c->stream));
-  if (val_bc_out) HF_TRY(val_bc_out->alloc(c->nnz, c->stream));
-  DevBuf<int> bad;
-  HF_TRY(bad.alloc(1, c->stream));
-  const int g = (c->Npad + 255) / 256;
-  k_diag_scale<<<g, 256, 0, c->stream>>>(c->N, c->Npad, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
-                                         op.scale.p, bad.p);
-  k_fill_sell<<<g, 256, 0, c->stream>>>(c->N, c->Npad, op.R, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
-                                        op.scale.p, op.slice_ptr.p, lcol_csr.p, op.col.p, op.lcol.p, op.val.p,
-                                        val_bc_out ? val_bc_out->p : nullptr);
-  HF_CUDA(cudaGetLastError());
-  int hbad = 0;
-  HF_TRY(bad.download(&hbad, 1, c->stream));   // also orders the kernels before lcol_csr is freed
-  if (hbad) return hf_fail(HF_ERR_STATE, "operator has a non-positive diagonal at row " + std::to_string(hbad - 1) +
-                                             " (unset material or degenerate cell?)");
   if (c->ws.parts.n < (size_t)4 * c->sm_count) HF_TRY(c->ws.parts.alloc((size_t)4 * c->sm_count, c->stream));
+  HF_TRY(sell_fill_values(c, csr_val, apply_bc, op, val_bc_out));
+  op.struct_valid = true;
   return HF_OK;
 }
 
@@ -605,15 +615,18 @@ extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
   cudaSetDevice(c->device);
   c->dt = dt;
   c->axisym = (c->nv == 3) ? (axisymmetric ? 1 : 0) : 0;
-  HF_TRY(c->valM.alloc(c->nnz, c->stream));
-  HF_TRY(c->valA0.alloc(c->nnz, c->stream));
+  if (c->valM.n != (size_t)c->nnz) HF_TRY(c->valM.alloc(c->nnz, c->stream));
+  if (c->valA0.n != (size_t)c->nnz) HF_TRY(c->valA0.alloc(c->nnz, c->stream));
   HF_TRY(cell_coefs(c, 1.0, 0.0));
   HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valM.p));
   HF_TRY(cell_coefs(c, 1.0, dt));
   HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, c->axisym, c->valA0.p));
+  const bool new_structure = !c->opA.struct_valid;
   HF_TRY(hf_build_sell(c, c->valA0, true, c->opA, &c->valA));
-  HF_TRY(hf_patch_plan(c, c->opA));
-  if (!c->opA.pp_rpt) HF_TRY(hf_persist_plan(c, c->opA));
+  if (new_structure) {
+    HF_TRY(hf_patch_plan(c, c->opA));
+    if (!c->opA.pp_rpt) HF_TRY(hf_persist_plan(c, c->opA));
+  }
   c->valM1.release();
   c->op_built = true;
   c->proj_built = false;
@@ -1116,8 +1129,10 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 0.0, c->ck.p);
     HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, 1, vals.p));
     HF_TRY(hf_build_sell(c, vals, false, c->opMr, nullptr));
-    HF_TRY(hf_patch_plan(c, c->opMr));
-    if (!c->opMr.pp_rpt) HF_TRY(hf_persist_plan(c, c->opMr));
+    if (!c->opMr.pp_rpt && !c->opMr.p_spw) {
+      HF_TRY(hf_patch_plan(c, c->opMr));
+      if (!c->opMr.pp_rpt) HF_TRY(hf_persist_plan(c, c->opMr));
+    }
     HF_TRY(c->proj_b.alloc((size_t)2 * c->Npad, c->stream));
     HF_TRY(c->proj_g.alloc((size_t)2 * c->N, c->stream));
     c->proj_built = true;

@@ -126,6 +126,8 @@ struct SellOp {
   int R = 0, nchunks = 0, halo_max = 0, mat_cap = 0, halo_cap = 0, nstages = 0;
   size_t stage_bytes = 0;
   DevBuf<unsigned short> lcol;
+  DevBuf<unsigned short> lcol_csr;     // the same local columns in CSR slot order (input of the value fill)
+  bool struct_valid = false;           // slices / patches / plans match the current mesh (values may be refilled)
   DevBuf<int> halo_ptr, halo_idx;
   size_t iter_smem = 0;
   SellView view() const { return SellView{nslices, slice_ptr.p, col.p, val.p}; }
