@@ -178,9 +178,10 @@ def iter_bytes(n, nnz):
     return 10.0 * nnz + 4.0 * n / 32 + 64.0 * n
 
 
-def configured_solver(case, device, rtol, warm=0.0, mode=0, ordering="auto", recycle=0):
+def configured_solver(case, device, rtol, warm=0.0, mode=0, ordering="auto", recycle=0, sharing=1):
     from heatflow_b200.solver import HeatSolver
     s = HeatSolver(device)
+    s.set_sharing(sharing)
     s.set_ordering(ordering)
     s.set_mesh(case.nodes, case.tris, case.cell_tag)
     s.set_materials(case.tags, case.kappa_t, case.rhoc_t)
@@ -307,21 +308,40 @@ def run_ours(args, rank, world, local_rank):
         i_sample = [m.name for m in c.mats].index("p_sample")
         sweep_engine = "serial" if s.on_chip() else "ensemble"
         if sweep_engine == "serial":
-            se = configured_solver(c, local_rank, args.rtol, warm=args.warm_start, recycle=args.recycle)
+            # the sweep engine's concurrent mode: two contexts planned with hf_set_sharing(2), one host thread each
+            workers = [configured_solver(c, local_rank, args.rtol, warm=args.warm_start, recycle=args.recycle, sharing=2)
+                       for _ in range(2)]
+            if workers[0].solver_path() != 3:              # does not fit with half an SM per CTA: one plain context
+                for w_ in workers:
+                    w_.close()
+                workers = [configured_solver(c, local_rank, args.rtol, warm=args.warm_start, recycle=args.recycle)]
+            sweep_engine = f"serial x{len(workers)}"
 
-            def sweep_pass(n_steps):
+            def sweep_worker(se, mine, n_steps):
                 k_now = None
-                for kv, cf in zip(ks, coeffs):
-                    if k_now != kv:
+                for i in mine:
+                    if k_now != ks[i]:
                         kap = c.kappa_t.copy()
-                        kap[i_sample] = kv
+                        kap[i_sample] = ks[i]
                         se.set_materials(c.tags, kap, c.rhoc_t)
                         se.build_operator(c.dt, True)
-                        k_now = kv
+                        k_now = ks[i]
                     se.set_state(u0)
-                    se.run(c.amps[:n_steps], c.ic, cf, watch)
+                    se.run(c.amps[:n_steps], c.ic, coeffs[i], watch)
+
+            def sweep_pass(n_steps):
+                th = [threading.Thread(target=sweep_worker, args=(se, range(j, B, len(workers)), n_steps))
+                      for j, se in enumerate(workers)]
+                for t_ in th:
+                    t_.start()
+                for t_ in th:
+                    t_.join()
+
+            def sweep_close():
+                for w_ in workers:
+                    w_.close()
         else:
-            se = configured_solver(c, local_rank, args.rtol, warm=args.warm_start, ordering="hilbert")
+            se = configured_solver(c, local_rank, args.rtol, warm=args.warm_start, recycle=args.recycle, ordering="hilbert")
             sample_tag = int(c.tags[i_sample])
 
             def sweep_pass(n_steps):
@@ -329,6 +349,9 @@ def run_ours(args, rank, world, local_rank):
                 se.ens_create(ks, coeffs, sample_tag)
                 se.ens_run(c.amps[:n_steps], c.ic, watch)
                 se.ens_destroy()
+
+            def sweep_close():
+                se.close()
         sweep_pass(min(steps, 8))                                  # warm-up
         barrier()
         t0 = time.perf_counter()
@@ -336,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         sweep_ms = (time.perf_counter() - t0) * 1e3
         barrier()
-        se.close()
+        sweep_close()
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, sweep_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -399,9 +422,9 @@ def run_ours(args, rank, world, local_rank):
     if sweep_ms > 0.0:
         line["sweep"] = {"sims_per_s": world * 16 / (sweep_ms * 1e-3), "variants": world * 16, "variants_per_gpu": 16, "steps": steps,
                          "engine": sweep_engine, "dof_timesteps_per_s": world * 16 * n * steps / (sweep_ms * 1e-3),
-                         "note": "one tile of 16 variants (2 conductivities x 8 widths) per GPU through the sweep engine, wall "
-                                 "clock incl. operator re-assembly (max over ranks); the 4096-variant sweep of config #5 is "
-                                 "256 such tiles"}
+                         "note": "one tile of 16 variants (2 conductivities x 8 widths) per GPU through the sweep engine (serial x2: "
+                                 "two simulations share the SMs, hf_set_sharing), wall clock incl. operator re-assembly (max "
+                                 "over ranks); the 4096-variant sweep of config #5 is 256 such tiles"}
     # >= 1 M-dof mesh (north_star target for the SpMV roofline): BASELINE config #4, konopkova cfg refined x 0.35
     if not args.skip_large:
         from helpers import build_case

@@ -39,6 +39,7 @@ SIGNATURES = {
     "hf_set_solver": (C.c_int, [_vp, _f64, _i32, _f64, _i32]),
     "hf_set_recycle": (C.c_int, [_vp, _i32]),
     "hf_get_solver_path": (C.c_int, [_vp]),
+    "hf_set_sharing": (C.c_int, [_vp, _i32]),
     "hf_set_profile": (C.c_int, [_vp, _i32]),
     "hf_get_solve_profile": (C.c_int, [_vp, _vp, _vp]),
     "hf_step": (C.c_int, [_vp, _i32, _f64, _f64, _f64, C.POINTER(_i32), C.POINTER(_f64)]),

@@ -625,7 +625,7 @@ extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
   HF_TRY(hf_build_sell(c, c->valA0, true, c->opA, &c->valA));
   if (new_structure) {
     HF_TRY(hf_patch_plan(c, c->opA));
-    if (!c->opA.pp_rpt) HF_TRY(hf_persist_plan(c, c->opA));
+    if (!c->opA.pp_rpt && c->share == 1) HF_TRY(hf_persist_plan(c, c->opA));   // that kernel needs a whole SM
   }
   c->valM1.release();
   c->op_built = true;
@@ -983,6 +983,17 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
     c->last_iters = hit[n_steps - 1];
     if (nfail) return hf_fail(HF_ERR_NOCONV, "PCG hit the iteration cap in " + std::to_string(nfail) + " of " +
                                                  std::to_string(n_steps) + " time steps");
+  }
+  return HF_OK;
+}
+
+extern "C" int hf_set_sharing(hf_ctx* c, int32_t n_concurrent) {
+  if (!c || n_concurrent < 1 || n_concurrent > 2) return hf_fail(HF_ERR_ARG, "hf_set_sharing: n_concurrent must be 1 or 2");
+  if (c->share != n_concurrent) {      // the kernel plans depend on it
+    c->share = n_concurrent;
+    c->opA.struct_valid = c->opMr.struct_valid = false;
+    c->opA.pp_rpt = c->opA.p_spw = c->opMr.pp_rpt = c->opMr.p_spw = 0;
+    c->op_built = c->proj_built = false;
   }
   return HF_OK;
 }

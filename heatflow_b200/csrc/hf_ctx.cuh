@@ -117,7 +117,7 @@ struct SellOp {
   size_t p_smem = 0;
   DevBuf<int2> p_range;                // per CTA: [lo, hi) column range of its rows
   // plan of the patch-based persistent kernel (hf_patch.cu); pp_rpt == 0 => not eligible
-  int pp_rpt = 0, pp_grid = 0, pp_mat_cap = 0, pp_halo_cap = 0;
+  int pp_rpt = 0, pp_grid = 0, pp_mat_cap = 0, pp_halo_cap = 0, pp_share = 1;
   size_t pp_smem = 0;
   DevBuf<unsigned short> pp_lcol;      // local columns for chunks of 256 * pp_rpt rows, sliced-ELL order
   DevBuf<int> pp_halo_ptr, pp_halo_idx;
@@ -212,6 +212,7 @@ struct hf_ctx {
   bool have_prev = false, have_source = false;
   // solver
   double rtol = 1e-14, warm = 0.0;
+  int share = 1;                       // hf_set_sharing: solves expected to run concurrently on this device (1 or 2)
   int max_iters = 20000, mode = 0, last_iters = 0;
   // counters (hf_get_stats)
   double stat_run_ms = 0.0, stat_relres = 0.0;

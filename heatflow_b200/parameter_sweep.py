@@ -154,14 +154,27 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
     _, stack = _runner_for(cfg0)
     with suppress_output(suppress_print):
         sim = Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device)
+    extra = []
     try:
+        # serial engine on an on-chip mesh: two simulations share the SMs (hf_set_sharing) when the mesh
+        # still fits with half the registers / shared memory per CTA
+        n_mine = sum(len(t) for t in tiles)
+        if engine in ("auto", "serial") and n_mine > 1 and sim.solver.on_chip():
+            with suppress_output(suppress_print):
+                sim.set_sharing(2)
+                if sim.solver.solver_path() == 3:
+                    extra.append(Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device, sharing=2))
+                else:
+                    sim.set_sharing(1)
         watch = sim.watcher_nodes(list(get_watcher_points(cfg0).values()))
         fwhm = np.array([c['fwhm'] for c in combinations])
         k = np.array([c['k'] for c in combinations])
-        out = sweep.run_tiles(sim, fwhm, k, tiles, watch, engine=engine)
+        out = sweep.run_tiles(sim, fwhm, k, tiles, watch, engine=engine, extra_sims=extra)
         return out + (sim.step_t.copy(),)
     finally:
         sim.close()
+        for e in extra:
+            e.close()
 
 
 def _device_worker(args):

@@ -104,9 +104,10 @@ def prepare_mesh(cfg, stack, mesh_folder, rebuild_mesh):
 
 def configure_solver(domain, cell_tags, materials, mat_tag_map, bcs, gaussian_bc, dt, device=0,
                      rtol=DEFAULT_RTOL, max_iters=DEFAULT_MAX_ITERS, ic_temp=None, warm=DEFAULT_WARM,
-                     recycle=DEFAULT_RECYCLE):
+                     recycle=DEFAULT_RECYCLE, sharing=1):
     """HeatSolver with mesh, DG0 tables, Dirichlet sets and the assembled operator."""
     solver = HeatSolver(device)
+    solver.set_sharing(sharing)
     nodes = domain.geometry.x[:, :2]
     solver.set_mesh(nodes, domain.cells, cell_tags.values)
     tags = [mat_tag_map[m.name] for m in materials]
@@ -126,7 +127,7 @@ class Simulation2D:
     (set-up half of the reference runners, run_with_diamond.py:183-394)."""
 
     def __init__(self, cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, device=0,
-                 rtol=DEFAULT_RTOL, max_iters=DEFAULT_MAX_ITERS):
+                 rtol=DEFAULT_RTOL, max_iters=DEFAULT_MAX_ITERS, sharing=1):
         self.cfg = cfg
         self.materials, self.info, self.domain, self.cell_tags, self.mat_tag_map = prepare_mesh(
             cfg, stack, mesh_folder, rebuild_mesh)
@@ -161,7 +162,7 @@ class Simulation2D:
         self.obj_bcs = problem.standard_bcs(V, p_coupler.boundaries[0], r_sample, ic_temp, gaussian)
         self.inner_bc = self.obj_bcs[3]
         self.solver = configure_solver(domain, cell_tags, materials, mat_tag_map, self.obj_bcs, self.inner_bc, dt,
-                                       device=device, rtol=rtol, max_iters=max_iters, ic_temp=ic_temp)
+                                       device=device, rtol=rtol, max_iters=max_iters, ic_temp=ic_temp, sharing=sharing)
         self.n_dofs = domain.geometry.x.shape[0]
         self.mesh_coords = domain.geometry.x[:, :2]
         self.step_t = (np.arange(num_steps) + 1) * dt
@@ -176,6 +177,11 @@ class Simulation2D:
 
     def sample_tag(self, name="p_sample"):
         return int(self.mat_tag_map[name])
+
+    def set_sharing(self, n_concurrent):
+        """Re-plan the on-chip kernel for ``n_concurrent`` simulations sharing the GPU (sweep engine)."""
+        self.solver.set_sharing(n_concurrent)
+        self.solver.build_operator(self.dt, axisymmetric=True)
 
     def set_conductivity(self, name, k):
         """Re-assemble the operator with material ``name`` at conductivity ``k`` (sweep variants)."""

@@ -188,6 +188,11 @@ class HeatSolver:
         _lib.check(self._L.hf_get_stats(self._h, _lib.ptr(st)))
         return {"run_ms": st[0], "launches": int(st[1]), "iterations": int(st[2]), "relres": st[3]}
 
+    def set_sharing(self, n_concurrent):
+        """Plan the on-chip kernel for ``n_concurrent`` (1 or 2) simulations sharing the GPU (call before
+        ``build_operator``); used by the sweep engine, which drives two contexts from two threads."""
+        _lib.check(self._L.hf_set_sharing(self._h, int(n_concurrent)))
+
     def set_profile(self, on=True):
         """CUDA events around every PCG solve of ``run`` (see ``solve_profile``)."""
         _lib.check(self._L.hf_set_profile(self._h, 1 if on else 0))

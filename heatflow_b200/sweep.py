@@ -45,42 +45,66 @@ def plan_tiles(k_values, batch, world_size):
     return [cut[r::world_size] for r in range(world_size)]
 
 
-def run_tiles_serial(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample"):
+def run_tiles_serial(sims, fwhm, k, tiles, watch_nodes, sample_name="p_sample"):
     """``run_tiles`` through the single-simulation path: same arguments, same return value
-    (iters = PCG iterations of the variant itself, seconds = wall time of the variant)."""
-    s = sim.solver
-    S, W = sim.num_steps, len(watch_nodes)
-    idx_all, hist_all, it_all, sec_all, errors = [], [], [], [], {}
-    k_now = None
-    u0 = np.full(sim.n_dofs, sim.ic_temp)
-    for tile in tiles:
-        for i in np.asarray(tile, dtype=np.int64):
+    (iters = PCG iterations of the variant itself, seconds = wall time of the variant).
+
+    ``sims``: one ``Simulation2D`` or a list of them on the same device.  With two (each planned with
+    ``sharing=2``) the variants are pulled from a common queue by two host threads, one context and stream
+    each: the on-chip kernels of the two simulations are co-resident and hide each other's reduction
+    latency (the C calls release the GIL)."""
+    import threading
+    sims = list(sims) if isinstance(sims, (list, tuple)) else [sims]
+    S, W = sims[0].num_steps, len(watch_nodes)
+    todo = [int(i) for tile in tiles for i in np.asarray(tile, dtype=np.int64)]
+    out, errors, lock, cursor = {}, {}, threading.Lock(), [0]
+    k_arr, f_arr = np.asarray(k, dtype=np.float64), np.asarray(fwhm, dtype=np.float64)
+
+    def worker(sim):
+        s = sim.solver
+        k_now = None
+        u0 = np.full(sim.n_dofs, sim.ic_temp)
+        while True:
+            with lock:
+                if cursor[0] >= len(todo):
+                    return
+                i = todo[cursor[0]]
+                cursor[0] += 1
             t0 = time.time()
             try:
-                ki = float(np.asarray(k)[i])
+                ki = float(k_arr[i])
                 if k_now != ki:
                     k_now = None                      # a failed re-assembly must not be mistaken for this k
                     sim.set_conductivity(sample_name, ki)
                     k_now = ki
                 s.set_state(u0)
-                hist, iters, _ = s.run(sim.amps, sim.ic_temp, problem.gaussian_coeff(float(np.asarray(fwhm)[i])), watch_nodes)
+                hist, iters, _ = s.run(sim.amps, sim.ic_temp, problem.gaussian_coeff(float(f_arr[i])), watch_nodes)
                 its = int(iters.sum())
             except Exception as exc:                   # recorded per run, as the reference does
-                errors[int(i)] = str(exc)
+                with lock:
+                    errors[i] = str(exc)
                 hist = np.full((S, W), np.nan)
                 its = -1
-            idx_all.append(int(i))
-            hist_all.append(hist)
-            it_all.append(its)
-            sec_all.append(time.time() - t0)
-    if not idx_all:
+            with lock:
+                out[i] = (hist, its, time.time() - t0)
+
+    if len(sims) == 1:
+        worker(sims[0])
+    else:
+        threads = [threading.Thread(target=worker, args=(sim,)) for sim in sims]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if not todo:
         return (np.zeros(0, np.int64), np.zeros((0, S, W)), np.zeros(0, np.int64), np.zeros(0), errors)
-    return (np.asarray(idx_all, dtype=np.int64), np.stack(hist_all).reshape(len(idx_all), S, W),
-            np.asarray(it_all, dtype=np.int64), np.asarray(sec_all), errors)
+    return (np.asarray(todo, dtype=np.int64), np.stack([out[i][0] for i in todo]).reshape(len(todo), S, W),
+            np.asarray([out[i][1] for i in todo], dtype=np.int64), np.asarray([out[i][2] for i in todo]), errors)
 
 
-def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample", engine="ensemble"):
-    """Advance every tile on ``sim.solver``'s device.
+def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample", engine="ensemble", extra_sims=()):
+    """Advance every tile on ``sim.solver``'s device (``extra_sims``: further simulations on the same
+    device for the concurrent serial engine).
 
     ``fwhm`` / ``k``: arrays over ALL variants; ``tiles``: index arrays owned by this rank.
     Returns (indices [P_local], hist [P_local, S, n_watch], iters [P_local] (PCG iterations of the
@@ -91,7 +115,7 @@ def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample", engine="
         raise ValueError("engine must be 'auto', 'ensemble' or 'serial'")
     s = sim.solver
     if engine == "serial" or (engine == "auto" and s.on_chip()):
-        return run_tiles_serial(sim, fwhm, k, tiles, watch_nodes, sample_name)
+        return run_tiles_serial([sim, *extra_sims], fwhm, k, tiles, watch_nodes, sample_name)
     S, W = sim.num_steps, len(watch_nodes)
     idx_all, hist_all, it_all, sec_all, errors = [], [], [], [], {}
     for tile in tiles:

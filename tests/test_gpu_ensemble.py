@@ -187,3 +187,53 @@ def test_ensemble_with_recycled_initial_guess_matches_oracle(wd, ks, fw, cap):
         assert iters.sum() < 0.6 * it0.sum()
     s.ens_destroy()
     s.close()
+
+
+def test_two_simulations_sharing_the_gpu_match_sequential_runs(wd):
+    # hf_set_sharing(2): two contexts driven from two host threads run their on-chip kernels concurrently;
+    # every simulation must give the answer it gives alone (1e-10 vs the oracle, ~1e-12 between kernels)
+    import threading
+    c = wd
+    S = 40
+    watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 3e-8, 0.0), (0.95e-6, 0.0)])
+    fws = [2e-6, 7e-6, 1.3e-5, 4e-5, 9e-5, 3e-6]
+    ref = make_solver(c, warm=1.0, recycle=64)
+    assert ref.solver_path() == 3
+    alone = []
+    for f in fws:
+        ref.set_state(np.full(len(c.nodes), c.ic))
+        h, _, _ = ref.run(c.amps[:S], c.ic, problem.gaussian_coeff(f), watch)
+        alone.append(h)
+    ref.close()
+    from heatflow_b200.solver import HeatSolver
+    pair = []
+    for _ in range(2):
+        s = HeatSolver(0)
+        s.set_sharing(2)
+        s.set_mesh(c.nodes, c.tris, c.cell_tag)
+        s.set_materials(c.tags, c.kappa_t, c.rhoc_t)
+        s.set_bcs(c.bc_dofs, c.bc_value, c.gauss_slot, c.gauss_r)
+        s.build_operator(c.dt, True)
+        s.set_solver(rtol=1e-14, warm=1.0)
+        s.set_recycle(64)
+        assert s.solver_path() == 3
+        pair.append(s)
+    got = {}
+
+    def work(s, mine):
+        for i in mine:
+            s.set_state(np.full(len(c.nodes), c.ic))
+            got[i], _, _ = s.run(c.amps[:S], c.ic, problem.gaussian_coeff(fws[i]), watch)
+
+    th = [threading.Thread(target=work, args=(pair[j], range(j, len(fws), 2))) for j in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i, f in enumerate(fws):
+        assert np.abs(got[i] / alone[i] - 1).max() <= 1e-11, i
+    O = oracle_variant(c, float(c.kappa_t[[m.name for m in c.mats].index("p_sample")]), fws[2])
+    oh, _ = O.run(S, watch)
+    assert np.abs(got[2] / oh - 1).max() <= RTOL_FIELD
+    with pytest.raises(_lib.HeatflowError):
+        pair[0].set_sharing(3)
+    for s in pair:
+        s.close()
