@@ -134,12 +134,13 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
   FxState fx;
   {
     const int ci = lane & 3, cr = lane >> 2;
-#pragma unroll
-    for (int set = 0; set < 2; ++set) {
-      const unsigned long long* q0 = P.acc_prev + ((size_t)set * HF_NREP + cr) * HF_ACC_LINE + 2 * ci;
-      fx.prev[set][0] = (warp == 0 && ci < 3 && cr < HF_NREP) ? q0[0] : 0ull;
-      fx.prev[set][1] = (warp == 0 && ci < 3 && cr < HF_NREP) ? q0[1] : 0ull;
-    }
+    const bool mine = warp == 0 && ci < 3 && cr < HF_NREP;
+    const unsigned long long* q0 = P.acc_prev + (size_t)cr * HF_ACC_LINE + 2 * ci;
+    const unsigned long long* q1 = q0 + (size_t)HF_NREP * HF_ACC_LINE;
+    fx.hi0 = mine ? q0[0] : 0ull;
+    fx.lo0 = mine ? q0[1] : 0ull;
+    fx.hi1 = mine ? q1[0] : 0ull;
+    fx.lo1 = mine ? q1[1] : 0ull;
   }
 #endif
   while (!done && it < P.max_it) {
@@ -273,12 +274,12 @@ __global__ void __launch_bounds__(HF_PT, 1) k_pcg_persist(PersistArgs P) {
 #if HF_RED_MODE == 1
   if (blockIdx.x == 0 && warp == 0 && (lane & 3) < 3 && (lane >> 2) < HF_NREP) {   // accumulator values the next launch starts from
     const int ci = lane & 3, cr = lane >> 2;
-#pragma unroll
-    for (int set = 0; set < 2; ++set) {
-      unsigned long long* q0 = P.acc_prev + ((size_t)set * HF_NREP + cr) * HF_ACC_LINE + 2 * ci;
-      q0[0] = fx.prev[set][0];
-      q0[1] = fx.prev[set][1];
-    }
+    unsigned long long* q0 = P.acc_prev + (size_t)cr * HF_ACC_LINE + 2 * ci;
+    unsigned long long* q1 = q0 + (size_t)HF_NREP * HF_ACC_LINE;
+    q0[0] = fx.hi0;
+    q0[1] = fx.lo0;
+    q1[0] = fx.hi1;
+    q1[1] = fx.lo1;
   }
 #endif
   if (blockIdx.x == 0 && tid == 0) {

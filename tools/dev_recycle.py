@@ -6,6 +6,13 @@ import numpy as np
 if os.environ.get("HF_DEV_LIB"):
     from heatflow_b200 import _lib as _l
     _l.LIB_PATH = os.path.abspath(os.environ["HF_DEV_LIB"])
+    import ctypes as _C                                   # older builds: drop the entry points they lack
+    _raw = _C.CDLL(_l.LIB_PATH)
+    for _name in [n for n in _l.SIGNATURES if not hasattr(_raw, n)]:
+        del _l.SIGNATURES[_name]
+    from heatflow_b200 import solver as _s
+    if "hf_set_sharing" not in _l.SIGNATURES:
+        _s.HeatSolver.set_sharing = lambda self, n: None
 from helpers import build_case, make_solver, make_oracle
 
 def probe(name, scale, steps, caps, mode=0, check=True):
