@@ -243,8 +243,12 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its version banner
+    # there at NCCL_DEBUG=VERSION / WARN) goes to stderr for the whole run
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("HF_NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     c = build(rank)
     n = len(c.nodes)
@@ -443,7 +447,8 @@ def run_ours(args, rank, world, local_rank):
                                           f"(SuperLU, sequential) factorised once outside the loop "
                                           f"(assembly {t_asm:.2f} s, factorisation {t_fac:.2f} s); host has {os.cpu_count()} cores"}
     line["parity_check"] = {"e2e_equals_device_run": bool(np.array_equal(hist, hist2))}
-    print(json.dumps(line), flush=True)
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     s.close()
     if world > 1:
         dist.destroy_process_group()
