@@ -110,3 +110,61 @@ def test_final_gather_gloo_world_size_2(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert ok.read_text() == "ok"
+
+
+class _FakeSolver:
+    """Stands in for HeatSolver in the host-side tests of the serial sweep engine (no GPU)."""
+
+    def __init__(self, log):
+        self.log, self.k = log, None
+
+    def set_state(self, u0):
+        self.u0 = float(u0[0])
+
+    def run(self, amps, t_ic, coeff, watch_nodes):
+        import time as _t
+        _t.sleep(0.002)
+        if coeff < -1e17:
+            raise RuntimeError("diverged")
+        S, W = len(amps), len(watch_nodes)
+        return np.full((S, W), self.k * 1000.0 + coeff), np.full(S, 7, dtype=np.int32), None
+
+
+class _FakeSim:
+    def __init__(self, log):
+        self.solver = _FakeSolver(log)
+        self.num_steps, self.n_dofs, self.ic_temp = 5, 11, 300.0
+        self.amps = np.arange(5.0)
+        self.log = log
+
+    def set_conductivity(self, name, k):
+        self.log.append((id(self), k))
+        self.solver.k = k
+
+
+@pytest.mark.parametrize("workers", [1, 2])
+def test_serial_engine_queue_results_and_errors(workers):
+    # variants are pulled from one queue by `workers` threads; results come back in tile order whatever thread
+    # ran them, a failing variant is recorded and does not stop the others, k changes re-assemble per worker
+    from heatflow_b200 import problem
+    log = []
+    sims = [_FakeSim(log) for _ in range(workers)]
+    k = np.array([1.0, 1.0, 2.0, 2.0, 2.0, 3.0, 3.0])
+    fwhm = np.array([1e-6, 2e-6, 3e-6, 4e-6, 5e-6, 6e-6, 1e-9])       # the last one "diverges" (huge |coeff|)
+    tiles = sweep.plan_tiles(k, 3, 1)[0]
+    idx, hist, iters, secs, errors = sweep.run_tiles_serial(sims, fwhm, k, tiles, [4, 9])
+    assert idx.tolist() == [int(i) for t in tiles for i in t] and hist.shape == (7, 5, 2)
+    for pos, i in enumerate(idx):
+        if i == 6:
+            assert i in errors and "diverged" in errors[i] and np.isnan(hist[pos]).all() and iters[pos] == -1
+        else:
+            assert np.allclose(hist[pos], k[i] * 1000.0 + problem.gaussian_coeff(fwhm[i])) and iters[pos] == 35
+    assert set(errors) == {6} and np.all(secs > 0)
+    # every worker re-assembles only when the conductivity it sees changes
+    per_worker = {}
+    for wid, kv in log:
+        per_worker.setdefault(wid, []).append(kv)
+    assert all(len(v) <= 3 and all(a != b for a, b in zip(v, v[1:])) for v in per_worker.values())
+    # empty share
+    out = sweep.run_tiles_serial(sims, fwhm, k, [], [4, 9])
+    assert out[0].size == 0 and out[1].shape == (0, 5, 2)
