@@ -548,9 +548,10 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   // chunk size of the streaming kernel (one persistent CTA per SM walks the chunks): 512 rows when every
   // CTA still gets >= 8 chunks, else 256
   op.R = (c->Npad >= 8 * c->sm_count * 512) ? 512 : 256;
+  if (HF_IT < 512) op.R = 256;                     // one row per thread in phase 1
   if (const char* env = getenv("HF_CHUNK_R")) {   // tuning knob
     const int r = atoi(env);
-    if (r == 256 || r == 512) op.R = r;
+    if (r == 256 || (r == 512 && HF_IT >= 512)) op.R = r;
   }
   op.nchunks = (c->Npad + op.R - 1) / op.R;
   op.mat_cap = 0;
@@ -568,6 +569,7 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   {
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+    max_smem = max_smem / HF_IT_MINB - 1024;         // HF_IT_MINB co-resident CTAs share the SM's shared memory
     op.nstages = (int)std::min<size_t>(4, ((size_t)max_smem - 2048) / op.stage_bytes);
     if (const char* env = getenv("HF_STAGES")) op.nstages = std::max(1, std::min(op.nstages, atoi(env)));
     if (op.nstages < 1)
@@ -586,7 +588,7 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
   HF_TRY(op.lcol.alloc(op.padded_nnz, c->stream));
   HF_TRY(op.val.alloc(op.padded_nnz, c->stream));
   HF_TRY(op.scale.alloc(c->Npad, c->stream));
-  if (c->ws.parts.n < (size_t)4 * c->sm_count) HF_TRY(c->ws.parts.alloc((size_t)4 * c->sm_count, c->stream));
+  if (c->ws.parts.n < (size_t)16 * c->sm_count) HF_TRY(c->ws.parts.alloc((size_t)16 * c->sm_count, c->stream));
   HF_TRY(sell_fill_values(c, csr_val, apply_bc, op, val_bc_out));
   op.struct_valid = true;
   return HF_OK;

@@ -12,6 +12,12 @@
 #define HF_BLOCK 256          // threads per CTA of the streaming kernels (8 warps)
 #define HF_SLICE 32           // rows per sliced-ELL slice = one warp, one row per lane
 #define HF_MAX_PART 2368      // max CTAs of a reduction-producing kernel (148 SMs x 16)
+#ifndef HF_IT
+#define HF_IT 256             // threads per CTA of the streaming PCG kernel (hf_pcg.cu)
+#endif
+#ifndef HF_IT_MINB
+#define HF_IT_MINB 3           // its CTAs per SM
+#endif
 
 extern thread_local std::string hf_err_msg;
 int hf_fail(int code, const std::string& msg);

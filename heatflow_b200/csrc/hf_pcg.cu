@@ -120,7 +120,10 @@ __device__ __forceinline__ void hf_issue_chunk(const PatchView& A, int ch, int e
                      stream);
 }
 
-#define HF_IT 512              // threads per CTA of the iteration kernel
+// threads per CTA and CTAs per SM of the iteration kernel (hf_ctx.cuh: HF_IT = 256, HF_IT_MINB = 3): three
+// small CTAs per SM, each with its own 2-stage TMA pipeline over chunks of 256 rows, overlap the per-chunk
+// latency (barrier -> phase 1 -> barrier -> phase 2) that one 512-thread CTA per SM exposes: 27.4 -> 21.0 us
+// per iteration at 5e5 dofs, 35.3 -> 31.8 us at 1.16 M dofs (measured)
 
 // Persistent: one CTA per SM walks the chunks blockIdx.x, blockIdx.x + gridDim.x, ...; the operator
 // block and the own-row vectors of the next chunks stream into the other shared-memory stages by TMA
@@ -128,7 +131,7 @@ __device__ __forceinline__ void hf_issue_chunk(const PatchView& A, int ch, int e
 // (chunk j: values, chunk j+1: node indices, chunk j+2: list extents), so no global-load latency is
 // exposed inside the chunk loop.
 template <int R>
-__global__ void __launch_bounds__(HF_IT, 1)
+__global__ void __launch_bounds__(HF_IT, HF_IT_MINB)
 k_pcg_iter(PatchView A, int par, IterStage S, double* __restrict__ x, double* __restrict__ rb0, double* __restrict__ rb1,
            double* __restrict__ pb0, double* __restrict__ pb1, double* __restrict__ qb0, double* __restrict__ qb1,
            double* __restrict__ parts, HfCtrl* __restrict__ c) {
@@ -406,8 +409,8 @@ static int launch_iteration(hf_ctx* c, const SellOp& op, int par) {
   PcgWork& w = c->ws;
   const PatchView A = op.patch();
   const IterStage S{op.mat_cap, op.halo_cap, op.nstages, (unsigned)op.stage_bytes};
-  const int grid = std::min(op.nchunks, c->sm_count);
-  if (op.R == 512)
+  const int grid = std::min(op.nchunks, c->sm_count * HF_IT_MINB);
+  if (op.R == 512 && HF_IT >= 512)
     k_pcg_iter<512><<<grid, HF_IT, op.iter_smem, c->stream>>>(A, par, S, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
   else
     k_pcg_iter<256><<<grid, HF_IT, op.iter_smem, c->stream>>>(A, par, S, w.x.p, w.r.p, w.r1.p, w.p0.p, w.p1.p, w.q.p, w.q1.p, w.parts.p, w.ctrl.p);
@@ -417,7 +420,7 @@ static int launch_iteration(hf_ctx* c, const SellOp& op, int par) {
 static int set_iter_smem(const SellOp& op) {
   // per function, not per operator: raise the limit right before use
   const int sm = (int)op.iter_smem;
-  if (op.R == 512) HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  if (op.R == 512 && HF_IT >= 512) HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   else HF_CUDA(cudaFuncSetAttribute(k_pcg_iter<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   return HF_OK;
 }
