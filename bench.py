@@ -136,6 +136,27 @@ def _reference_worker(job):
     return len(c.nodes), t_loop, t_asm, t_fac
 
 
+def _cpu_sweep_worker(job):
+    """One sweep variant the way the reference runs it (parameter_sweep.py:123-192): assemble, factorise, time loop."""
+    index, steps = job
+    os.environ["OMP_NUM_THREADS"] = "1"
+    c = build(index + 1)                                  # mesh re-used per width group in the reference: not timed
+    t0 = time.perf_counter()
+    _t_loop, _t_asm, _t_fac, _ = oracle_loop(c, steps, 0)
+    return time.perf_counter() - t0
+
+
+def cpu_sweep_baseline(steps):
+    """Sweep throughput of the CPU arm: one single-threaded process per variant on every host core (bounded sample)."""
+    import multiprocessing as mp
+    procs = max(1, min(os.cpu_count() or 1, 16))
+    with mp.get_context("spawn").Pool(processes=procs) as pool:
+        secs = pool.map(_cpu_sweep_worker, [(i, steps) for i in range(procs)])
+    return {"sims_per_s": procs / max(secs), "cores": procs, "kind": "port",
+            "sample": f"{procs} variants in {procs} single-threaded processes at once, each assembling, factorising (scipy splu) "
+                      f"and running {steps} steps (mesh generation not timed); slowest process {max(secs):.1f} s"}
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port (scipy sparse LU) on the box's host cores.  Like our arm at N GPUs it runs N
     independent simulations (sweep variant = index), one single-threaded process each - the reference's own
@@ -446,6 +467,8 @@ def run_ours(args, rank, world, local_rank):
                                 "sample": f"{cb_steps} time steps of the same simulation after 1 warm-up step, scipy splu "
                                           f"(SuperLU, sequential) factorised once outside the loop "
                                           f"(assembly {t_asm:.2f} s, factorisation {t_fac:.2f} s); host has {os.cpu_count()} cores"}
+    if not args.skip_cpu and "sweep" in line:
+        line["sweep"]["cpu_baseline"] = cpu_sweep_baseline(steps)
     line["parity_check"] = {"e2e_equals_device_run": bool(np.array_equal(hist, hist2))}
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()
