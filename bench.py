@@ -150,8 +150,11 @@ def cpu_sweep_baseline(steps):
     """Sweep throughput of the CPU arm: one single-threaded process per variant on every host core (bounded sample)."""
     import multiprocessing as mp
     procs = max(1, min(os.cpu_count() or 1, 16))
-    with mp.get_context("spawn").Pool(processes=procs) as pool:
-        secs = pool.map(_cpu_sweep_worker, [(i, steps) for i in range(procs)])
+    try:
+        with mp.get_context("spawn").Pool(processes=procs) as pool:
+            secs = pool.map_async(_cpu_sweep_worker, [(i, steps) for i in range(procs)]).get(timeout=240)
+    except Exception as exc:                                # a reported baseline must never hang or fail the bench
+        return {"sims_per_s": None, "cores": procs, "kind": "port", "sample": f"not measured: {type(exc).__name__}"}
     return {"sims_per_s": procs / max(secs), "cores": procs, "kind": "port",
             "sample": f"{procs} variants in {procs} single-threaded processes at once, each assembling, factorising (scipy splu) "
                       f"and running {steps} steps (mesh generation not timed); slowest process {max(secs):.1f} s"}
