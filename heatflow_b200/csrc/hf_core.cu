@@ -934,6 +934,26 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
     if (w.step_iters.n < (size_t)n_steps) HF_TRY(w.step_iters.alloc(n_steps, c->stream));
     HF_CUDA(cudaMemsetAsync(w.fail.p, 0, sizeof(int), c->stream));
   }
+  // per-step field output (XDMF): pin the caller's buffer for the duration of the run so that the copies
+  // are asynchronous DMA transfers that overlap the next step instead of staged synchronous ones
+  struct HostPin {                                        // unpins on every exit path, after the stream has drained
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    ~HostPin() {
+      if (p) {
+        cudaStreamSynchronize(s);
+        cudaHostUnregister(p);
+      }
+    }
+  } pin;
+  if (fields && n_steps > 0) {
+    if (cudaHostRegister(fields, sizeof(double) * (size_t)n_steps * c->N, cudaHostRegisterDefault) == cudaSuccess) {
+      pin.p = fields;
+      pin.s = c->stream;
+    } else {
+      cudaGetLastError();                                 // not fatal: pageable copies still work
+    }
+  }
   c->stat_solve_ms = 0.0;
   c->stat_solve_launches = 0;
   if (c->profile)
