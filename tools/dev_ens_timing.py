@@ -8,6 +8,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+if os.environ.get("HF_DEV_LIB"):
+    from heatflow_b200 import _lib as _l
+    _l.LIB_PATH = os.path.abspath(os.environ["HF_DEV_LIB"])
 from helpers import build_case, make_solver  # noqa: E402
 from heatflow_b200 import problem  # noqa: E402
 
