@@ -25,31 +25,34 @@
 
 #include "hf_ctx.cuh"
 
-#define RC_SEG 1024           // rows per CTA of the dot-product kernel
+#ifndef RC_SEG
+#define RC_SEG 512            // rows per CTA of the dot-product kernel (two CTAs per SM at 1.4e5 dofs: their load /
+#endif                        // reduce phases overlap; 1024 rows per CTA was 3 % slower end to end)
+#define RC_NV (RC_SEG / 64)    // 16-byte loads per lane and basis vector
 #define RC_WARPS 8
 
-// parts[k * nseg + seg] = sum over the 1024 rows of segment `seg` of V[k][i] * v[i], k < m
+// parts[k * nseg + seg] = sum over the RC_SEG rows of segment `seg` of V[k][i] * v[i], k < m
 // (vector m_extra is read from `extra` instead of its slot).
-// One CTA per segment; every lane keeps its 32 values of v in registers (2 x 16 consecutive-pair
+// One CTA per segment; every lane keeps its RC_SEG / 32 values of v in registers (consecutive-pair
 // loads) and the warps share the basis vectors (warp w takes k = w, w + 8, ...), so each warp has
-// sixteen independent 512-byte loads in flight per basis vector and no barrier is needed.
+// RC_SEG / 64 independent 512-byte loads in flight per basis vector and no barrier is needed.
 __global__ void __launch_bounds__(RC_WARPS * 32)
 k_rc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double* __restrict__ v,
           double* __restrict__ parts, int m_extra, const double* __restrict__ extra) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int seg = blockIdx.x;
   const size_t base = (size_t)seg * RC_SEG + 2 * lane;
-  double2 vv[16];
+  double2 vv[RC_NV];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) vv[j] = *reinterpret_cast<const double2*>(v + base + 64 * j);
+  for (int j = 0; j < RC_NV; ++j) vv[j] = *reinterpret_cast<const double2*>(v + base + 64 * j);
   for (int k = warp; k < m; k += RC_WARPS) {
     const double* p = ((k == m_extra) ? extra : V + (size_t)k * ld) + base;   // the pending raw correction is not in a slot yet
-    double2 a[16];
+    double2 a[RC_NV];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = __ldcs(reinterpret_cast<const double2*>(p + 64 * j));
+    for (int j = 0; j < RC_NV; ++j) a[j] = __ldcs(reinterpret_cast<const double2*>(p + 64 * j));
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < RC_NV; ++j) {
       s0 = fma(a[j].x, vv[j].x, s0);
       s1 = fma(a[j].y, vv[j].y, s1);
     }
