@@ -156,6 +156,7 @@ extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const do
   c->op_built = c->proj_built = false;
   c->opA.struct_valid = c->opMr.struct_valid = false;
   c->opA.pp_rpt = c->opA.p_spw = c->opMr.pp_rpt = c->opMr.p_spw = 0;
+  c->opMr.plan_from = nullptr;
   // ---- internal numbering.  auto: triangle meshes are sorted along a Hilbert curve so that consecutive
   // rows form compact 2-D patches with short halo lists (patch kernel, streaming kernel, ensembles); the
   // caller's (banded) order is kept on request (hf_set_ordering(ctx, 1): contiguous-range kernel) and for
@@ -834,19 +835,21 @@ __global__ void k_sample(int n, const int* __restrict__ nodes, const double* __r
 }
 
 // 0 = streaming graph chunks (host polls), 1 = persistent single-launch kernel
+static bool has_patch_plan(const SellOp& op) { return op.pp_rpt != 0 || (op.plan_from && op.plan_from->pp_rpt != 0); }
+
 static int pick_persist(hf_ctx* c, const SellOp& op, bool* persist) {
   // a specific on-chip kernel was requested: plan it on demand
-  if (c->mode == 3 && !op.pp_rpt) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));
+  if (c->mode == 3 && !has_patch_plan(op)) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));
   if (c->mode == 2 && !op.p_spw) HF_TRY(hf_persist_plan(c, const_cast<SellOp&>(op)));
-  if ((c->mode == 2 && !op.p_spw) || (c->mode == 3 && !op.pp_rpt))
+  if ((c->mode == 2 && !op.p_spw) || (c->mode == 3 && !has_patch_plan(op)))
     return hf_fail(HF_ERR_STATE, "an on-chip PCG kernel was requested (solver mode 2 / 3) but the mesh does not fit on chip");
-  *persist = (c->mode >= 2) || (c->mode == 0 && (op.pp_rpt != 0 || op.p_spw != 0));
+  *persist = (c->mode >= 2) || (c->mode == 0 && (has_patch_plan(op) || op.p_spw != 0));
   return HF_OK;
 }
 
 // one cooperative launch per solve: auto prefers the patch kernel (faster at every size it fits)
 static int solve_on_chip(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts) {
-  if (c->mode == 2 || !op.pp_rpt) return hf_pcg_solve_async(c, op, step_slot, sum_parts);
+  if (c->mode == 2 || !has_patch_plan(op)) return hf_pcg_solve_async(c, op, step_slot, sum_parts);
   return hf_patch_solve_async(c, op, step_slot, sum_parts);
 }
 
@@ -946,7 +949,8 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
       }
     }
   } pin;
-  if (fields && n_steps > 0) {
+  // (page-locking costs ~10 ms per call: only worth it when several steps' worth of fields come back)
+  if (fields && n_steps >= 4) {
     if (cudaHostRegister(fields, sizeof(double) * (size_t)n_steps * c->N, cudaHostRegisterDefault) == cudaSuccess) {
       pin.p = fields;
       pin.s = c->stream;
@@ -1015,6 +1019,7 @@ extern "C" int hf_set_sharing(hf_ctx* c, int32_t n_concurrent) {
     c->share = n_concurrent;
     c->opA.struct_valid = c->opMr.struct_valid = false;
     c->opA.pp_rpt = c->opA.p_spw = c->opMr.pp_rpt = c->opMr.p_spw = 0;
+  c->opMr.plan_from = nullptr;
     c->op_built = c->proj_built = false;
   }
   return HF_OK;
@@ -1162,7 +1167,9 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     k_fill<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, 0.0, c->ck.p);
     HF_TRY(hf_assemble_values(c, c->cm.p, c->ck.p, 1, vals.p));
     HF_TRY(hf_build_sell(c, vals, false, c->opMr, nullptr));
-    if (!c->opMr.pp_rpt && !c->opMr.p_spw) {
+    if (c->opA.pp_rpt) {
+      c->opMr.plan_from = &c->opA;               // same sparsity pattern: same patches, halo lists, local columns
+    } else if (!c->opMr.pp_rpt && !c->opMr.p_spw) {
       HF_TRY(hf_patch_plan(c, c->opMr));
       if (!c->opMr.pp_rpt) HF_TRY(hf_persist_plan(c, c->opMr));
     }

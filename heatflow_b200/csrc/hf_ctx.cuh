@@ -128,6 +128,7 @@ struct SellOp {
   DevBuf<unsigned short> pp_lcol;      // local columns for chunks of 256 * pp_rpt rows, sliced-ELL order
   DevBuf<int> pp_halo_ptr, pp_halo_idx;
   DevBuf<unsigned char> pp_pub;        // rows whose q packet some other CTA reads
+  const SellOp* plan_from = nullptr;   // patch plan borrowed from an operator with the same sparsity pattern
   // patch decomposition (streaming kernel)
   int R = 0, nchunks = 0, halo_max = 0, mat_cap = 0, halo_cap = 0, nstages = 0;
   size_t stage_bytes = 0;

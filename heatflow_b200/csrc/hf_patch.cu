@@ -432,13 +432,14 @@ int hf_patch_plan(hf_ctx* c, SellOp& op) {
   return HF_OK;
 }
 
-int hf_patch_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts) {
+int hf_patch_solve_async(hf_ctx* c, const SellOp& vals, int step_slot, bool sum_parts) {
   PcgWork& w = c->ws;
+  const SellOp& op = vals.plan_from ? *vals.plan_from : vals;     // plan (patches) may be borrowed; values are the operator's own
   if (!op.pp_rpt) return hf_fail(HF_ERR_STATE, "patch PCG kernel is not available for this mesh size");
   PatchArgs a;
-  a.nslices = op.nslices;
-  a.slice_ptr = op.slice_ptr.p;
-  a.val = op.val.p;
+  a.nslices = vals.nslices;
+  a.slice_ptr = vals.slice_ptr.p;
+  a.val = vals.val.p;
   a.lcol = op.pp_lcol.p;
   a.halo_ptr = op.pp_halo_ptr.p;
   a.halo_idx = op.pp_halo_idx.p;

@@ -239,21 +239,21 @@ def run_2d(cfg, stack, mesh_folder, rebuild_mesh=False, visualize_mesh=False, ou
         print('Beginning loop...')
         startup_time = time.time() - program_start_time
         step_t, amps = sim.step_t, sim.amps
-        per_step_host_work = write_xdmf or radial_outputs
+        # whole progress intervals run on the device without host round trips.  XDMF fields come back through
+        # hf_run's pinned field buffer (asynchronous copies that overlap the next steps) and are written per
+        # interval; only the gradient CSV rows need a projection solve and a host round trip after every step.
+        max_chunk = max(1, (1 << 27) // max(1, n_dofs))          # <= 1 GB of fields on the host at a time
         step = 0
         while step < num_steps:
-            # whole progress intervals run on the device without host round trips unless a
-            # per-step output (XDMF field, gradient CSV row) needs the state on the host
-            chunk = 1 if per_step_host_work else min(progress_interval - (step % progress_interval), num_steps - step)
+            chunk = 1 if radial_outputs else min(progress_interval - (step % progress_interval), num_steps - step, max_chunk)
             t0 = time.time()
-            hist, iters, _ = solver.run(amps[step:step + chunk], ic_temp, coeff, watcher_nodes)
-            if per_step_host_work:
-                t = step_t[step]
-                if radial_outputs:
-                    grad.record(t, solver.project_gradient())
-                if write_xdmf:
-                    u_n.x.array[:] = solver.get_state()
-                    xdmf.write_function(u_n, t)
+            hist, iters, fields = solver.run(amps[step:step + chunk], ic_temp, coeff, watcher_nodes, keep_fields=write_xdmf)
+            if radial_outputs:
+                grad.record(step_t[step], solver.project_gradient())
+            if write_xdmf:
+                for k in range(chunk):
+                    u_n.x.array[:] = fields[k]
+                    xdmf.write_function(u_n, step_t[step + k])
             elapsed = time.time() - t0
             for k in range(chunk):
                 if watcher_points is not None:
