@@ -354,3 +354,41 @@ def test_large_mesh_size_independent_properties():
     assert np.abs(h1 / h0 - 1).max() <= 1e-11 and np.abs(s.get_state() / u_plain - 1).max() <= 1e-11
     assert it1.sum() < it0.sum()
     s.close()
+
+
+def test_edge_cases_empty_runs_tiny_mesh_and_iteration_cap(small_nd):
+    from heatflow_b200._lib import HeatflowError
+    from heatflow_b200.solver import HeatSolver
+    c = small_nd
+    s = make_solver(c)
+    # empty run / no watchers: nothing moves, shapes are right
+    u_before = s.get_state()
+    hist, iters, _ = s.run(c.amps[:0], c.ic, c.coeff, [0])
+    assert hist.shape == (0, 1) and iters.shape == (0,) and np.array_equal(s.get_state(), u_before)
+    hist, iters, _ = s.run(c.amps[10:13], c.ic, c.coeff, [])
+    assert hist.shape == (3, 0) and np.all(iters > 0)
+    # iteration cap: reported as an error, never a silent wrong answer
+    s.set_solver(rtol=1e-14, max_iters=5)
+    with pytest.raises(HeatflowError, match="iteration|converge"):
+        s.run(c.amps[20:22], c.ic, c.coeff, [0])
+    s.close()
+    # a two-triangle mesh with constant Dirichlet data only (no Gaussian dofs): one patch, one CTA
+    nodes = np.array([[0.0, 0.0], [1e-6, 0.0], [1e-6, 1e-6], [0.0, 1e-6]])
+    tris = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    t = HeatSolver(0)
+    t.set_mesh(nodes, tris, np.array([1, 1], dtype=np.int32))
+    t.set_materials([1], [10.0], [3.0e6])
+    t.set_bcs([0, 3], [300.0, 300.0])
+    t.build_operator(1e-7, True)
+    t.set_solver(rtol=1e-14)
+    t.set_recycle(4)
+    t.set_state(np.array([300.0, 500.0, 500.0, 300.0]))
+    O = ho.Oracle2D(nodes, tris, np.full(2, 3.0e6), np.full(2, 10.0), 1e-7, [(np.array([0, 3]), "const")], 300.0, 1e-6,
+                    np.array([0.0, 1.0]), np.array([300.0, 300.0]))
+    O.u = np.array([300.0, 500.0, 500.0, 300.0])
+    for k in range(6):
+        t.step(None)
+        ou = O.step((k + 1) * 1e-7)
+        assert np.abs(t.get_state() / ou - 1).max() <= RTOL_FIELD
+    assert np.all(t.get_state()[[1, 2]] < 500.0)
+    t.close()
