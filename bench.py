@@ -20,6 +20,7 @@ Extra objects on the JSON line:
   roofline_1m   ``k_pcg_iter`` (streaming kernel, one launch per PCG iteration) on the >= 1 M-dof
                 refinement of ``cfgs/konopkova.yaml`` (BASELINE config #4), timed inside a real solve:
                 CUDA events around the step loop / launches, so launch gaps count against it.
+  roofline_4m   the same on a 4.3 M-dof refinement: 580 MB per iteration, far beyond the L2.
   sweep         tile of 16 (k, fwhm) variants per GPU through the sweep engine's path -> sims/s.
   cpu_baseline  the scipy sparse-LU oracle on this host (1 core), bounded sample.
 """
@@ -480,6 +481,8 @@ def run_ours(args, rank, world, local_rank):
         line["roofline_1m"] = streaming_roofline(cl, local_rank, args.rtol, peak, peak_src, steps=3,
                                                  traffic=traffic.get("k_pcg_iter_1m"))
         line["konopkova_1m"] = large_mesh_run(cl, local_rank, args.rtol, args.warm_start, min(args.recycle, 64))
+        # DRAM-honest: 4.3 M dofs, 580 MB per PCG iteration - nothing survives in the 126 MB L2 between iterations
+        line["roofline_4m"] = streaming_roofline(build_case("konopkova", 0.18), local_rank, args.rtol, peak, peak_src, steps=2)
         # the size of the reference's own gmsh meshes (2.1e5 - 4.3e5 nodes): still on chip
         line["mid_mesh"] = large_mesh_run(build_case(WORKLOAD, 0.6), local_rank, args.rtol, args.warm_start, args.recycle)
     # CPU baseline on this host (bounded sample)
