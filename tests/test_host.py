@@ -156,3 +156,21 @@ def test_runner_file_contract(tmp_path):
         prepare_mesh(cfg, problem.stack_no_diamond, str(folder), False)
     assert run_with_diamond.run_simulation.__code__.co_varnames[:8] == (
         "cfg", "mesh_folder", "rebuild_mesh", "visualize_mesh", "output_folder", "watcher_points", "write_xdmf", "suppress_print")
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    # the CPU arm of bench.py runs without a GPU: one JSON line with the keys the round contract names
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("DOF-timesteps/sec") and d["unit"] == "DOF-timesteps/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
