@@ -159,16 +159,7 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_patch(PatchArgs P) {
   bool done = !(rr > thr);
   double pp = rr;                                // magnitude estimate of ||p||^2, see hf_persist.cu
   FxState fx;
-  {
-    const int ci = lane & 3, cr = lane >> 2;
-    const bool mine = warp == 0 && ci < 3 && cr < HF_NREP;
-    const unsigned long long* q0 = P.acc_prev + (size_t)cr * HF_ACC_LINE + 2 * ci;
-    const unsigned long long* q1 = q0 + (size_t)HF_NREP * HF_ACC_LINE;
-    fx.hi0 = mine ? q0[0] : 0ull;
-    fx.lo0 = mine ? q0[1] : 0ull;
-    fx.hi1 = mine ? q1[0] : 0ull;
-    fx.lo1 = mine ? q1[1] : 0ull;
-  }
+  hf_fx_load_state(fx, P.acc_prev);
   while (!done && it < P.max_it) {
     ++gen;
     uint4* qout = P.qpk + (size_t)(it & 1) * P.npad;   // double buffered by iteration parity
@@ -287,15 +278,7 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_patch(PatchArgs P) {
 #pragma unroll
   for (int k = 0; k < RPT; ++k)
     if (wid[k] >= 0) P.x[lo + (warp * RPT + k) * 32 + lane] = x[k];
-  if (blockIdx.x == 0 && warp == 0 && (lane & 3) < 3 && (lane >> 2) < HF_NREP) {
-    const int ci = lane & 3, cr = lane >> 2;
-    unsigned long long* q0 = P.acc_prev + (size_t)cr * HF_ACC_LINE + 2 * ci;
-    unsigned long long* q1 = q0 + (size_t)HF_NREP * HF_ACC_LINE;
-    q0[0] = fx.hi0;
-    q0[1] = fx.lo0;
-    q1[0] = fx.hi1;
-    q1[1] = fx.lo1;
-  }
+  hf_fx_store_state(fx, P.acc_prev);   // accumulator values the next launch starts from
   if (blockIdx.x == 0 && tid == 0) {
     P.c->rr = rr;
     P.c->itA = it;

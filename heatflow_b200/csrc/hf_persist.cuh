@@ -107,7 +107,7 @@ __device__ __forceinline__ void hf_grid_wait(double (&out)[NV], uint4* slots, in
 #define HF_RED_MODE 1    // 0: packet slots, CTA 0 reduces and broadcasts (two L2 trips); 1: fixed-point atomics (one trip)
 #endif
 #ifndef HF_NREP
-#define HF_NREP 8        // replicated accumulator lines (spreads the atomics of the G CTAs); <= 8 (4 polling lanes each)
+#define HF_NREP 8        // replicated accumulator lines (spread the atomics of the G CTAs); a multiple of 8
 #endif
 #ifndef HF_POLL_DELAY
 // cycles the polling warp waits before its first load: the total cannot be complete sooner than one trip through
@@ -140,8 +140,9 @@ __device__ __forceinline__ void hf_grid_wait(double (&out)[NV], uint4* slots, in
 // Values of this lane's chunk (hi and lo word) when each set was last complete.  Plain scalars selected with
 // predicates: an array indexed by the generation parity ends up in local memory, and its loads and stores
 // sit on the critical path of every reduction.
+#define HF_RPL ((HF_NREP + 7) / 8)   // replicas per polling lane (lane l polls value l & 3 of replicas (l >> 2) + 8 j)
 struct FxState {
-  unsigned long long hi0, lo0, hi1, lo1;
+  unsigned long long hi0[HF_RPL], lo0[HF_RPL], hi1[HF_RPL], lo1[HF_RPL];   // indexed by unrolled constants only
 };
 
 __device__ __forceinline__ void hf_red_add(unsigned long long* p, unsigned long long v) {
@@ -159,6 +160,38 @@ __device__ __forceinline__ double hf_scale2(double t, int k) {
   return t * __hiloint2double((1023 + k1) << 20, 0) * __hiloint2double((1023 + k2) << 20, 0);
 }
 __device__ __forceinline__ int hf_clamp_exp(int e) { return max(-900, min(900, e)); }
+
+// accumulator values when the previous launch ended (every CTA loads them; CTA 0 stores them back at the end)
+__device__ __forceinline__ void hf_fx_load_state(FxState& st, const unsigned long long* acc_prev) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ci = lane & 3;
+#pragma unroll
+  for (int j = 0; j < HF_RPL; ++j) {
+    const int r = (lane >> 2) + 8 * j;
+    const bool mine = warp == 0 && ci < 3 && r < HF_NREP;
+    const unsigned long long* q0 = acc_prev + (size_t)(mine ? r : 0) * HF_ACC_LINE + 2 * ci;
+    const unsigned long long* q1 = q0 + (size_t)HF_NREP * HF_ACC_LINE;
+    st.hi0[j] = mine ? q0[0] : 0ull;
+    st.lo0[j] = mine ? q0[1] : 0ull;
+    st.hi1[j] = mine ? q1[0] : 0ull;
+    st.lo1[j] = mine ? q1[1] : 0ull;
+  }
+}
+__device__ __forceinline__ void hf_fx_store_state(const FxState& st, unsigned long long* acc_prev) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ci = lane & 3;
+  if (blockIdx.x != 0 || warp != 0 || ci >= 3) return;
+#pragma unroll
+  for (int j = 0; j < HF_RPL; ++j) {
+    const int r = (lane >> 2) + 8 * j;
+    if (r < HF_NREP) {
+      unsigned long long* q0 = acc_prev + (size_t)r * HF_ACC_LINE + 2 * ci;
+      unsigned long long* q1 = q0 + (size_t)HF_NREP * HF_ACC_LINE;
+      q0[0] = st.hi0[j];
+      q0[1] = st.lo0[j];
+      q1[0] = st.hi1[j];
+      q1[1] = st.lo1[j];
+    }
+  }
+}
 
 template <int NV>
 __device__ __forceinline__ void hf_fx_arrive(const double (&v)[NV], const int (&eb)[NV], unsigned long long* acc, unsigned gen,
@@ -204,13 +237,20 @@ __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV
   double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
   if (warp == 0) {
     const int set = (int)(gen & 1u);
-    const int i = lane & 3, r = lane >> 2;
-    const int members = (r < G && r < HF_NREP) ? (G - 1 - r) / HF_NREP + 1 : 0;
-    const bool active = i < NV && members > 0;
-    const unsigned long long* chunk = acc + ((size_t)set * HF_NREP + r) * HF_ACC_LINE + 2 * i;
-    unsigned long long whi = 0ull, wlo = 0ull;
-    const unsigned long long phi = set ? st.hi1 : st.hi0, plo = set ? st.lo1 : st.lo0;
-    bool ok = !active;
+    const int i = lane & 3;
+    unsigned long long whi[HF_RPL], wlo[HF_RPL], phi[HF_RPL], plo[HF_RPL], mem[HF_RPL];
+    const unsigned long long* chunk[HF_RPL];
+    bool okj[HF_RPL];
+#pragma unroll
+    for (int j = 0; j < HF_RPL; ++j) {
+      const int r = (lane >> 2) + 8 * j;
+      mem[j] = (r < G && r < HF_NREP) ? (unsigned long long)((G - 1 - r) / HF_NREP + 1) : 0ull;
+      okj[j] = !(i < NV && mem[j] > 0ull);              // inactive lanes / replicas are complete by definition
+      chunk[j] = acc + ((size_t)set * HF_NREP + r) * HF_ACC_LINE + 2 * i;
+      phi[j] = set ? st.hi1[j] : st.hi0[j];
+      plo[j] = set ? st.lo1[j] : st.lo0[j];
+      whi[j] = wlo[j] = 0ull;
+    }
 #if HF_POLL_DELAY
     {                                                     // the sum cannot be complete sooner than one trip through L2
       const long long t0 = clock64();
@@ -218,23 +258,31 @@ __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV
     }
 #endif
     for (;;) {
-      if (!ok) {
-        hf_ld2(chunk, whi, wlo);
-        ok = ((whi - phi) & 0xffull) == (unsigned long long)members && ((wlo - plo) & 0xffull) == (unsigned long long)members;
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < HF_RPL; ++j)
+        if (!okj[j]) hf_ld2(chunk[j], whi[j], wlo[j]);
+#pragma unroll
+      for (int j = 0; j < HF_RPL; ++j) {
+        if (!okj[j]) okj[j] = ((whi[j] - phi[j]) & 0xffull) == mem[j] && ((wlo[j] - plo[j]) & 0xffull) == mem[j];
+        ok = ok && okj[j];
       }
       if (__all_sync(0xffffffffu, ok)) break;
     }
     long long shi = 0;
     unsigned long long slo = 0ull;
-    if (active) {
-      shi = (long long)(whi - phi - (unsigned long long)members) >> 8;
-      slo = (wlo - plo - (unsigned long long)members) >> 8;
-      if (set) {
-        st.hi1 = whi;
-        st.lo1 = wlo;
-      } else {
-        st.hi0 = whi;
-        st.lo0 = wlo;
+#pragma unroll
+    for (int j = 0; j < HF_RPL; ++j) {
+      if (i < NV && mem[j] > 0ull) {
+        shi += (long long)(whi[j] - phi[j] - mem[j]) >> 8;
+        slo += (wlo[j] - plo[j] - mem[j]) >> 8;
+        if (set) {
+          st.hi1[j] = whi[j];
+          st.lo1[j] = wlo[j];
+        } else {
+          st.hi0[j] = whi[j];
+          st.lo0[j] = wlo[j];
+        }
       }
     }
 #pragma unroll
