@@ -21,6 +21,20 @@ import numpy as np
 TRI3 = 2  # gmsh element type of the 3-node triangle
 
 
+def _rows_to_text(out, arr):
+    """Rows of a 2-D array as space-separated lines: integers verbatim, floats as the shortest repr that
+    round-trips (plain Python formatting of `tolist()` rows is ~2 x faster than np.savetxt here)."""
+    arr = np.asarray(arr)
+    if arr.ndim == 1:
+        arr = arr[:, None]
+    if arr.dtype.kind in "iu":
+        fmt = " ".join(["%d"] * arr.shape[1])
+        out.write("\n".join(fmt % tuple(r) for r in arr.tolist()))
+    else:
+        out.write("\n".join(" ".join(map(repr, r)) for r in arr.tolist()))
+    out.write("\n")
+
+
 def write_msh(path, nodes, tris, cell_tag, names):
     """``names``: dict physical tag -> name (tag == surface entity tag, as in the reference
     where both are numbered 1..n in material order, mesh.py:113-126)."""
@@ -49,17 +63,17 @@ def write_msh(path, nodes, tris, cell_tag, names):
     out.write(f"$Nodes\n{len(blocks)} {n_nodes} 1 {n_nodes}\n")
     for t, idx in blocks:
         out.write(f"2 {t} 0 {idx.size}\n")
-        np.savetxt(out, idx + 1, fmt="%d")
+        _rows_to_text(out, idx + 1)
         xyz = np.zeros((idx.size, 3))
         xyz[:, :2] = nodes[idx]
-        np.savetxt(out, xyz, fmt="%.17g")
+        _rows_to_text(out, xyz)
     out.write("$EndNodes\n")
     eblocks = [(t, np.flatnonzero(cell_tag == t)) for t in tags]
     out.write(f"$Elements\n{len(eblocks)} {n_tris} 1 {n_tris}\n")
     for t, idx in eblocks:
         out.write(f"2 {t} {TRI3} {idx.size}\n")
         rows = np.column_stack((idx + 1, tris[idx] + 1))
-        np.savetxt(out, rows, fmt="%d")
+        _rows_to_text(out, rows)
     out.write("$EndElements\n")
     with open(path, "w") as f:
         f.write(out.getvalue())
