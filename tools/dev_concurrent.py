@@ -11,7 +11,15 @@ from heatflow_b200 import problem
 nthreads = int(sys.argv[1]); nsim = int(sys.argv[2])
 c = build_case("geballe_with_diamond", 1.0)
 n = len(c.nodes)
-solvers = [make_solver(c, warm=1.0, recycle=128) for _ in range(nthreads)]
+from heatflow_b200.solver import HeatSolver
+def mk():
+    s = HeatSolver(0)
+    s.set_sharing(2 if nthreads > 1 else 1)
+    s.set_mesh(c.nodes, c.tris, c.cell_tag); s.set_materials(c.tags, c.kappa_t, c.rhoc_t)
+    s.set_bcs(c.bc_dofs, c.bc_value, c.gauss_slot, c.gauss_r); s.build_operator(c.dt, True)
+    s.set_solver(rtol=1e-14, warm=1.0); s.set_recycle(128)
+    return s
+solvers = [mk() for _ in range(nthreads)]
 fw = np.logspace(-6, -4, 64)
 def work(t):
     s = solvers[t]
