@@ -155,7 +155,7 @@ extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const do
   c->Npad = (N + HF_SLICE - 1) / HF_SLICE * HF_SLICE;
   c->op_built = c->proj_built = false;
   c->opA.struct_valid = c->opMr.struct_valid = false;
-  c->opA.pp_rpt = c->opA.p_spw = c->opMr.pp_rpt = c->opMr.p_spw = 0;
+  c->opA.pp_rpt = c->opMr.pp_rpt = 0;
   c->opMr.plan_from = nullptr;
   // ---- internal numbering.  auto: triangle meshes are sorted along a Hilbert curve so that consecutive
   // rows form compact 2-D patches with short halo lists (patch kernel, streaming kernel, ensembles); the
@@ -628,7 +628,6 @@ extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
   HF_TRY(hf_build_sell(c, c->valA0, true, c->opA, &c->valA));
   if (new_structure) {
     HF_TRY(hf_patch_plan(c, c->opA));
-    if (!c->opA.pp_rpt && c->share == 1) HF_TRY(hf_persist_plan(c, c->opA));   // that kernel needs a whole SM
   }
   c->valM1.release();
   c->op_built = true;
@@ -834,23 +833,30 @@ __global__ void k_sample(int n, const int* __restrict__ nodes, const double* __r
   if (i < n) out[i] = u[nodes[i]];
 }
 
-// 0 = streaming graph chunks (host polls), 1 = persistent single-launch kernel
+// Which PCG kernel solves with `op` (hf_get_solver_path): 1 = streaming kernel, one launch per iteration, the host
+// polls (k_pcg_iter); 2 = persistent streaming kernel, one cooperative launch per solve (k_pcg_stream); 3 = on-chip
+// patch kernel, one cooperative launch per solve (k_pcg_patch).  Paths 2 and 3 are fully asynchronous.
 static bool has_patch_plan(const SellOp& op) { return op.pp_rpt != 0 || (op.plan_from && op.plan_from->pp_rpt != 0); }
 
-static int pick_persist(hf_ctx* c, const SellOp& op, bool* persist) {
-  // a specific on-chip kernel was requested: plan it on demand
-  if (c->mode == 3 && !has_patch_plan(op)) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));
-  if (c->mode == 2 && !op.p_spw) HF_TRY(hf_persist_plan(c, const_cast<SellOp&>(op)));
-  if ((c->mode == 2 && !op.p_spw) || (c->mode == 3 && !has_patch_plan(op)))
-    return hf_fail(HF_ERR_STATE, "an on-chip PCG kernel was requested (solver mode 2 / 3) but the mesh does not fit on chip");
-  *persist = (c->mode >= 2) || (c->mode == 0 && (has_patch_plan(op) || op.p_spw != 0));
+static int pick_path(hf_ctx* c, const SellOp& op, int* path) {
+  const int mode = c->force_mode >= 0 ? c->force_mode : c->mode;
+  // a specific single-launch kernel was requested: plan it on demand
+  if (mode == 3 && !has_patch_plan(op)) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));
+  if (mode == 3 && !has_patch_plan(op))
+    return hf_fail(HF_ERR_STATE, "the on-chip PCG kernel was requested (solver mode 3) but the mesh does not fit on chip");
+  if ((mode == 2 || (mode == 0 && !has_patch_plan(op))) && !op.st_grid) HF_TRY(hf_stream_plan(c, const_cast<SellOp&>(op)));
+  if (mode == 2 && !op.st_grid)
+    return hf_fail(HF_ERR_STATE, "the persistent streaming PCG kernel was requested (solver mode 2) but cannot be launched "
+                                 "cooperatively on this device");
+  if (mode == 0) *path = has_patch_plan(op) ? 3 : (op.st_grid ? 2 : 1);
+  else *path = mode;
   return HF_OK;
 }
 
-// one cooperative launch per solve: auto prefers the patch kernel (faster at every size it fits)
-static int solve_on_chip(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts) {
-  if (c->mode == 2 || !has_patch_plan(op)) return hf_pcg_solve_async(c, op, step_slot, sum_parts);
-  return hf_patch_solve_async(c, op, step_slot, sum_parts);
+// one cooperative launch per solve
+static int solve_single_launch(hf_ctx* c, const SellOp& op, int path, int step_slot, bool sum_parts) {
+  if (path == 3) return hf_patch_solve_async(c, op, step_slot, sum_parts);
+  return hf_stream_solve_async(c, op, step_slot, sum_parts);
 }
 
 // Synchronous completion of a persistent solve: read the control-block header.
@@ -875,8 +881,9 @@ static int finish_sync(hf_ctx* c, int* iters, double* relres) {
 static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double coeff, int* iters, double* relres,
                        int step_slot, int prof_slot = -1) {
   if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_step: operator not built");
-  bool persist = false;
-  HF_TRY(pick_persist(c, c->opA, &persist));
+  int path = 1;
+  HF_TRY(pick_path(c, c->opA, &path));
+  const bool persist = path >= 2;
   c->stat_launches += 2 + ((use_gauss && c->n_gauss) ? 1 : 0);
   if (use_gauss && c->n_gauss)
     k_bc_gauss<<<(c->n_gauss + 255) / 256, 256, 0, c->stream>>>(c->n_gauss, c->gauss_dof.p, c->gauss_r.p, amp, t_ic, coeff,
@@ -894,7 +901,7 @@ static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double
   const unsigned long long l0 = c->stat_launches;
   if (prof) HF_CUDA(cudaEventRecord(c->prof_ev[2 * prof_slot], c->stream));
   if (persist) {
-    HF_TRY(solve_on_chip(c, c->opA, step_slot, true));
+    HF_TRY(solve_single_launch(c, c->opA, path, step_slot, true));
     if (step_slot < 0) HF_TRY(finish_sync(c, iters, relres));
   } else {
     HF_TRY(hf_pcg_solve(c, c->opA, iters, relres));
@@ -919,24 +926,57 @@ extern "C" int hf_step(hf_ctx* c, int32_t use_gauss, double amp, double t_ic, do
   return HF_OK;
 }
 
+// The time loop of hf_run on the device.  `path` >= 2: every step is one asynchronous cooperative solve, iteration
+// counts land in ws.step_iters, failures are counted in ws.fail; path 1: the host polls every solve.
+static int run_steps(hf_ctx* c, int path, int32_t n_steps, const double* amp, double t_ic, double coeff, int32_t n_watch,
+                     double* fields, int32_t* iters) {
+  const bool persist = path >= 2;
+  for (int s = 0; s < n_steps; ++s) {
+    int it = 0;
+    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr, persist ? s : -1, s));
+    if (iters && !persist) iters[s] = it;
+    if (n_watch) c->stat_launches += 1;
+    if (n_watch)
+      k_sample<<<(n_watch + 255) / 256, 256, 0, c->stream>>>(n_watch, c->watch.p, c->u.p, c->hist.p + (size_t)s * n_watch);
+    if (fields) {
+      // XDMF field output needs the state on the host after every step; the copy is stream ordered
+      const double* src = c->u.p;
+      if (c->permuted) {   // the staging buffer is reused only after the copy below has run
+        k_gather_nodal<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, 1, c->rank_d.p, c->u.p, c->stage.p);
+        src = c->stage.p;
+      }
+      HF_CUDA(cudaMemcpyAsync(fields + (size_t)s * c->N, src, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  return HF_OK;
+}
+
 extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic, double coeff, int32_t n_watch,
                       const int32_t* watch_nodes, double* hist, double* fields, int32_t* iters) {
   if (!c || n_steps < 0 || (n_steps && !amp) || n_watch < 0 || (n_watch && (!watch_nodes || !hist)))
     return hf_fail(HF_ERR_ARG, "hf_run: bad arguments");
   cudaSetDevice(c->device);
+  if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_run: operator not built");
   std::vector<int> wn;
   if (hf_internal_nodes(c, n_watch, watch_nodes, wn) != HF_OK) return hf_fail(HF_ERR_ARG, "hf_run: watch node out of range");
   if (n_watch) {
     HF_TRY(c->watch.upload(wn.data(), n_watch, c->stream));
     if (c->hist.n < (size_t)n_steps * n_watch) HF_TRY(c->hist.alloc((size_t)n_steps * n_watch, c->stream));
   }
-  bool persist = false;
-  HF_TRY(pick_persist(c, c->opA, &persist));
+  int path = 1;
+  HF_TRY(pick_path(c, c->opA, &path));
+  const bool persist = path >= 2;
   PcgWork& w = c->ws;
   if (persist) {
     if (w.step_iters.n < (size_t)n_steps) HF_TRY(w.step_iters.alloc(n_steps, c->stream));
     HF_CUDA(cudaMemsetAsync(w.fail.p, 0, sizeof(int), c->stream));
+    // state at the start of the run: a failed asynchronous solve is only seen at the end, and the run is then
+    // repeated from here with the host-polled streaming kernel (see below)
+    if (c->u0_keep.n != (size_t)2 * c->N) HF_TRY(c->u0_keep.alloc((size_t)2 * c->N, c->stream));
+    HF_CUDA(cudaMemcpyAsync(c->u0_keep.p, c->u.p, sizeof(double) * c->N, cudaMemcpyDeviceToDevice, c->stream));
+    HF_CUDA(cudaMemcpyAsync(c->u0_keep.p + c->N, c->uprev.p, sizeof(double) * c->N, cudaMemcpyDeviceToDevice, c->stream));
   }
+  const bool had_prev = c->have_prev;
   // per-step field output (XDMF): pin the caller's buffer for the duration of the run so that the copies
   // are asynchronous DMA transfers that overlap the next step instead of staged synchronous ones
   struct HostPin {                                        // unpins on every exit path, after the stream has drained
@@ -967,21 +1007,25 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
       c->prof_ev.push_back(e);
     }
   HF_CUDA(cudaEventRecord(c->ev0, c->stream));
-  for (int s = 0; s < n_steps; ++s) {
-    int it = 0;
-    // XDMF field output needs the state on the host after every step; the copy is stream ordered
-    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr, persist ? s : -1, s));
-    if (iters && !persist) iters[s] = it;
-    if (n_watch) c->stat_launches += 1;
-    if (n_watch)
-      k_sample<<<(n_watch + 255) / 256, 256, 0, c->stream>>>(n_watch, c->watch.p, c->u.p, c->hist.p + (size_t)s * n_watch);
-    if (fields) {
-      const double* src = c->u.p;
-      if (c->permuted) {   // stream-ordered: the staging buffer is reused only after the copy below has run
-        k_gather_nodal<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, 1, c->rank_d.p, c->u.p, c->stage.p);
-        src = c->stage.p;
-      }
-      HF_CUDA(cudaMemcpyAsync(fields + (size_t)s * c->N, src, sizeof(double) * c->N, cudaMemcpyDeviceToHost, c->stream));
+  HF_TRY(run_steps(c, path, n_steps, amp, t_ic, coeff, n_watch, fields, iters));
+  if (persist && n_steps) {
+    int nfail = 0;
+    HF_TRY(w.fail.download(&nfail, 1, c->stream));
+    if (nfail) {
+      // A single-launch solve hit its iteration cap or produced a non-finite residual (e.g. a partial sum outside the
+      // fixed-point range of the on-chip reduction).  The state it left behind is not trustworthy, so the whole run is
+      // repeated from its initial state with the host-polled streaming kernel, which reports failures per step -
+      // still the GPU path; if that fails as well the error is raised.
+      c->stat_retries += 1;
+      HF_CUDA(cudaMemcpyAsync(c->u.p, c->u0_keep.p, sizeof(double) * c->N, cudaMemcpyDeviceToDevice, c->stream));
+      HF_CUDA(cudaMemcpyAsync(c->uprev.p, c->u0_keep.p + c->N, sizeof(double) * c->N, cudaMemcpyDeviceToDevice, c->stream));
+      c->have_prev = had_prev;
+      hf_rc_reset(c);
+      c->force_mode = 1;
+      const int rc = run_steps(c, 1, n_steps, amp, t_ic, coeff, n_watch, fields, iters);
+      c->force_mode = -1;
+      if (rc != HF_OK) return rc;
+      path = 1;
     }
   }
   HF_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -997,18 +1041,14 @@ extern "C" int hf_run(hf_ctx* c, int32_t n_steps, const double* amp, double t_ic
       HF_CUDA(cudaEventElapsedTime(&t, c->prof_ev[2 * s], c->prof_ev[2 * s + 1]));
       c->stat_solve_ms += t;
     }
-  if (persist && n_steps) {
+  if (path >= 2 && n_steps) {
     std::vector<int> hit(n_steps);
-    int nfail = 0;
     HF_TRY(w.step_iters.download(hit.data(), n_steps, c->stream));
-    HF_TRY(w.fail.download(&nfail, 1, c->stream));
     for (int s = 0; s < n_steps; ++s) {
       if (iters) iters[s] = hit[s];
       c->stat_iters += hit[s];
     }
     c->last_iters = hit[n_steps - 1];
-    if (nfail) return hf_fail(HF_ERR_NOCONV, "PCG hit the iteration cap in " + std::to_string(nfail) + " of " +
-                                                 std::to_string(n_steps) + " time steps");
   }
   return HF_OK;
 }
@@ -1018,7 +1058,7 @@ extern "C" int hf_set_sharing(hf_ctx* c, int32_t n_concurrent) {
   if (c->share != n_concurrent) {      // the kernel plans depend on it
     c->share = n_concurrent;
     c->opA.struct_valid = c->opMr.struct_valid = false;
-    c->opA.pp_rpt = c->opA.p_spw = c->opMr.pp_rpt = c->opMr.p_spw = 0;
+    c->opA.pp_rpt = c->opMr.pp_rpt = 0;
   c->opMr.plan_from = nullptr;
     c->op_built = c->proj_built = false;
   }
@@ -1041,10 +1081,9 @@ extern "C" int hf_get_solve_profile(hf_ctx* c, double* solve_ms, int64_t* solve_
 extern "C" int hf_get_solver_path(hf_ctx* c) {
   if (!c) return hf_fail(HF_ERR_ARG, "null context");
   if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_get_solver_path: operator not built");
-  bool persist = false;
-  HF_TRY(pick_persist(c, c->opA, &persist));
-  if (!persist) return 1;
-  return (c->mode == 2 || !c->opA.pp_rpt) ? 2 : 3;
+  int path = 1;
+  HF_TRY(pick_path(c, c->opA, &path));
+  return path;
 }
 
 extern "C" int hf_get_stats(hf_ctx* c, double* st) {
@@ -1053,6 +1092,13 @@ extern "C" int hf_get_stats(hf_ctx* c, double* st) {
   st[1] = (double)c->stat_launches;
   st[2] = (double)c->stat_iters;
   st[3] = c->stat_relres;
+  st[4] = (double)c->stat_retries;
+  return HF_OK;
+}
+
+extern "C" int hf_debug_fx_shift(hf_ctx* c, int32_t bits) {
+  if (!c || bits < 0 || bits > 400) return hf_fail(HF_ERR_ARG, "hf_debug_fx_shift: bits must be in [0, 400]");
+  c->debug_fx_shift = bits;
   return HF_OK;
 }
 
@@ -1169,9 +1215,8 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     HF_TRY(hf_build_sell(c, vals, false, c->opMr, nullptr));
     if (c->opA.pp_rpt) {
       c->opMr.plan_from = &c->opA;               // same sparsity pattern: same patches, halo lists, local columns
-    } else if (!c->opMr.pp_rpt && !c->opMr.p_spw) {
+    } else if (!c->opMr.pp_rpt) {
       HF_TRY(hf_patch_plan(c, c->opMr));
-      if (!c->opMr.pp_rpt) HF_TRY(hf_persist_plan(c, c->opMr));
     }
     HF_TRY(c->proj_b.alloc((size_t)2 * c->Npad, c->stream));
     HF_TRY(c->proj_g.alloc((size_t)2 * c->N, c->stream));
@@ -1191,10 +1236,10 @@ extern "C" int hf_project_gradient(hf_ctx* c, double* grad, int32_t* iters_out) 
     HF_TRY(hf_pcg_prepare_from_r(c));
     int it = 0;
     c->last_iters = 40;
-    bool persist = false;
-    HF_TRY(pick_persist(c, c->opMr, &persist));
-    if (persist) {
-      HF_TRY(solve_on_chip(c, c->opMr, -1, false));
+    int path = 1;
+    HF_TRY(pick_path(c, c->opMr, &path));
+    if (path >= 2) {
+      HF_TRY(solve_single_launch(c, c->opMr, path, -1, false));
       HF_TRY(finish_sync(c, &it, nullptr));
     } else {
       HF_TRY(hf_pcg_solve(c, c->opMr, &it, nullptr));

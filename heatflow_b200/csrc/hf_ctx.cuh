@@ -118,10 +118,7 @@ struct SellOp {
   DevBuf<double> val;
   DevBuf<double> scale;                // s_i = sqrt(diag) (1 on Dirichlet rows)
   mutable cudaGraphExec_t chunk_exec[3] = {nullptr, nullptr, nullptr};   // captured PCG iteration chunks
-  // plan of the persistent (single-launch) PCG kernel; spw == 0 => not eligible
-  int p_spw = 0, p_grid = 0, p_mat_cap = 0, p_sz_cap = 0;
-  size_t p_smem = 0;
-  DevBuf<int2> p_range;                // per CTA: [lo, hi) column range of its rows
+  int st_grid = 0;                     // co-resident grid of the persistent streaming kernel (hf_stream.cu); 0 => not eligible
   // plan of the patch-based persistent kernel (hf_patch.cu); pp_rpt == 0 => not eligible
   int pp_rpt = 0, pp_grid = 0, pp_mat_cap = 0, pp_halo_cap = 0, pp_share = 1;
   size_t pp_smem = 0;
@@ -153,9 +150,10 @@ struct PcgWork {
   DevBuf<double> r1, q1;               // second halves of the ping-pong pairs (streaming kernel)
   DevBuf<double> parts;                // [4][max chunks] per-CTA partial sums (streaming kernel)
   DevBuf<HfCtrl> ctrl;
-  DevBuf<uint4> slots;                 // flag-with-data reduction slots (persistent kernel)
   DevBuf<unsigned long long> acc, acc_prev;   // fixed-point reduction accumulators (persistent kernel)
   DevBuf<uint4> qpk;                   // [2][Npad] q = A p exchange packets (persistent kernel)
+  DevBuf<double> sparts;               // [2][4][grid] per-CTA partial sums of the persistent streaming kernel
+  DevBuf<unsigned long long> bar;      // its grid barrier: arrival counter, value at the end of the last launch
   DevBuf<unsigned> gen;                // barrier generation, monotonic across launches
   DevBuf<int> step_iters;              // per-step iteration counts written by the persistent kernel
   DevBuf<int> fail;                    // number of solves that hit max_iters
@@ -221,6 +219,10 @@ struct hf_ctx {
   double rtol = 1e-14, warm = 0.0;
   int share = 1;                       // hf_set_sharing: solves expected to run concurrently on this device (1 or 2)
   int max_iters = 20000, mode = 0, last_iters = 0;
+  int debug_fx_shift = 0;              // hf_debug_fx_shift (tests): shrinks the fixed-point range of the on-chip reduction
+  int force_mode = -1;                 // >= 0: overrides `mode` (the retry of a failed single-launch run)
+  unsigned long long stat_retries = 0; // runs repeated with the host-polled kernel after a failed single-launch solve
+  DevBuf<double> u0_keep;              // [2N] u, uprev at the start of hf_run
   // counters (hf_get_stats)
   double stat_run_ms = 0.0, stat_relres = 0.0;
   unsigned long long stat_launches = 0, stat_iters = 0;
@@ -287,9 +289,9 @@ __device__ __forceinline__ int hf_ld_stream(const int* p) {
 // shared between translation units
 int hf_pcg_alloc(hf_ctx* c);
 int hf_pcg_solve(hf_ctx* c, const SellOp& op, int* iters_out, double* relres_out);
-int hf_persist_plan(hf_ctx* c, SellOp& op);
-int hf_pcg_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts = false);
 int hf_patch_plan(hf_ctx* c, SellOp& op);
+int hf_stream_plan(hf_ctx* c, SellOp& op);
+int hf_stream_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts = false);
 int hf_patch_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts = false);
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out);
 int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out);

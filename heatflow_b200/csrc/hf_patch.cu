@@ -1,8 +1,7 @@
 // heatflow_b200 - persistent cooperative Jacobi-PCG on compact patches (sm_100a).
 //
-// Same algorithm and communication scheme as hf_persist.cu (one launch per solve, q = Ahat p halo
-// packets, one exact fixed-point grid reduction per iteration), for meshes whose 148 x 1024-row
-// contiguous ghost ranges no longer fit on chip (reference meshes: 2e5 - 4e5 nodes).  With the
+// One launch per solve; neighbouring CTAs exchange q = Ahat p on their halo rows as flag-with-data packets and
+// there is one exact fixed-point grid reduction per iteration (hf_persist.cuh).  With the
 // Hilbert node order a CTA's R = 256 x RPT rows form a compact 2-D patch whose halo is a short list
 // (~4 sqrt(R) rows instead of two full mesh rows), so per row the CTA keeps
 //   operator   8 B value + 2 B local column per stored entry       (~85 B, sliced-ELL padding included)
@@ -38,6 +37,7 @@ struct PatchArgs {
   int max_it, npad, nparts;
   double rtol;
   int mat_cap, halo_cap;
+  int eb_shift;                  // diagnostics (hf_debug_fx_shift): subtracted from the fixed-point exponent bounds
 };
 
 // MINB = CTAs per SM the kernel is compiled for.  1: the whole register file of the SM caches operator rows
@@ -194,9 +194,9 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_patch(PatchArgs P) {
       }
     }
     const int e_pp = hf_exp2(pp), e_rr = hf_exp2(rr);
-    const int eb3[3] = {hf_clamp_exp(e_pp + 4 + HF_FX_MARGIN), hf_clamp_exp((e_rr + e_pp + 1) / 2 + 5 + HF_FX_MARGIN),
+    const int eb3[3] = {hf_clamp_exp(e_pp + 4 + HF_FX_MARGIN - P.eb_shift), hf_clamp_exp((e_rr + e_pp + 1) / 2 + 5 + HF_FX_MARGIN),
                         hf_clamp_exp(e_pp + 8 + HF_FX_MARGIN)};
-    hf_fx_arrive<3>(d, eb3, P.acc, gen, red);
+    hf_fx_arrive<3>(d, eb3, P.acc, gen, red, P.fail);
     // ---- halo q packets: warps >= 1 fetch them while warp 0 polls the reduction
     if (warp >= 1) {
       constexpr int NP = HF_PT - 32;
@@ -210,8 +210,13 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_patch(PatchArgs P) {
           g[t] = need[t] ? shal[h0 + t * NP] : 0;
         }
         bool pending;
+        int spins = 0;
         do {
           pending = false;
+          if (++spins > HF_SPIN_MAX) {                // a neighbour never published: give up loudly instead of hanging
+            atomicAdd(P.fail, 1);
+            break;
+          }
 #pragma unroll
           for (int t = 0; t < 4; ++t)
             if (need[t]) hq[t] = hf_pkt_load(qout + g[t]);
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_patch(PatchArgs P) {
       }
     }
     double tot[3];
-    hf_fx_wait<3>(tot, eb3, P.acc, G, gen, red, fx);
+    hf_fx_wait<3>(tot, eb3, P.acc, G, gen, red, fx, P.fail);
     const double alpha = rr / tot[0];
     double rr_new = fma(alpha * alpha, tot[2], fma(-2.0 * alpha, tot[1], rr));
     ++since_check;
@@ -259,8 +264,8 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_patch(PatchArgs P) {
       ++gen;
       double t1[1];
       const int eb1[1] = {hf_clamp_exp(max(e_rr, 2 * hf_exp2(fabs(alpha)) + 8 + e_pp) + 2 + HF_FX_MARGIN)};
-      hf_fx_arrive<1>(dd, eb1, P.acc, gen, red);
-      hf_fx_wait<1>(t1, eb1, P.acc, G, gen, red, fx);
+      hf_fx_arrive<1>(dd, eb1, P.acc, gen, red, P.fail);
+      hf_fx_wait<1>(t1, eb1, P.acc, G, gen, red, fx, P.fail);
       rr_new = t1[0];
       rr_ref = rr_new;
       since_check = 0;
@@ -442,6 +447,7 @@ int hf_patch_solve_async(hf_ctx* c, const SellOp& vals, int step_slot, bool sum_
   a.rtol = c->rtol;
   a.mat_cap = op.pp_mat_cap;
   a.halo_cap = op.pp_halo_cap;
+  a.eb_shift = c->debug_fx_shift;
   void* args[] = {&a};
   const void* fn = patch_kernel(op.pp_rpt, op.pp_share);
   HF_TRY(patch_set_smem_rpt(op.pp_rpt, op.pp_share, op.pp_smem));   // per function, not per operator

@@ -1,5 +1,5 @@
-// heatflow_b200 - device helpers shared by the persistent PCG kernels (hf_persist.cu, hf_patch.cu):
-// flag-with-data packets, the ordered packet-tree reduction and the one-trip fixed-point reduction.
+// heatflow_b200 - device helpers of the on-chip PCG kernel (hf_patch.cu): flag-with-data packets and the
+// one-trip fixed-point grid reduction.
 #pragma once
 #include "hf_ctx.cuh"
 
@@ -11,7 +11,9 @@
 #endif
 #define HF_PW (HF_PT / 32)
 static_assert(HF_PT == HF_BLOCK, "hf_sum_parts / hf_block_sum stride over HF_BLOCK threads");
-#define HF_SLOT_STRIDE 8   // uint4 per slot: one 128-byte line each
+#ifndef HF_SPIN_MAX
+#define HF_SPIN_MAX (1 << 23)   // polls before a spin loop gives up (seconds): the solve is then reported as failed
+#endif
 #define HF_MAX_GRID 160
 #define HF_RR_CHECK 64  // iterations between direct recomputations of ||r||^2
 #define HF_WR 8          // operator entries per row cached in registers
@@ -28,84 +30,6 @@ __device__ __forceinline__ uint4 hf_pkt_load(const uint4* p) {
 __device__ __forceinline__ bool hf_pkt_ok(const uint4& v, unsigned gen) { return v.y == gen && v.w == gen; }
 __device__ __forceinline__ double hf_pkt_val(const uint4& v) { return __hiloint2double((int)v.z, (int)v.x); }
 
-// Grid-wide sums of NV values per thread, split in two halves so that independent work can be
-// overlapped with the wait:  arrive = CTA reduction + publish,  wait = poll + broadcast.
-// Warp i (< NV) of every CTA handles value i.  CTA 0 is the reducer: it polls the other CTAs'
-// slots (all loads of a polling round in flight together), adds the partials in slot order and
-// broadcasts; the other CTAs poll the broadcast slot.  O(G) polling traffic per reduction.
-// Result: identical bits in every thread of every CTA.  No memory ordering is implied.
-template <int NV>
-__device__ __forceinline__ void hf_grid_arrive(const double (&v)[NV], uint4* slots, unsigned gen, double* red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const double t = hf_warp_sum(v[i]);
-    if (lane == 0) sh[warp * NV + i] = t;
-  }
-  __syncthreads();
-  if (warp < NV && blockIdx.x != 0) {
-    uint4* set = slots + (size_t)(gen & 1u) * (HF_MAX_GRID + 1) * HF_SLOT_STRIDE;
-    const double t = hf_warp_sum(lane < HF_PW ? sh[lane * NV + warp] : 0.0);
-    if (lane == 0) hf_pkt_store(set + (size_t)blockIdx.x * HF_SLOT_STRIDE + warp, t, gen);
-  }
-}
-
-template <int NV>
-__device__ __forceinline__ void hf_grid_wait(double (&out)[NV], uint4* slots, int G, unsigned gen, double* red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
-  uint4* set = slots + (size_t)(gen & 1u) * (HF_MAX_GRID + 1) * HF_SLOT_STRIDE;
-  uint4* bcast = set + (size_t)HF_MAX_GRID * HF_SLOT_STRIDE;
-  if (warp < NV) {
-    if (blockIdx.x != 0) {
-      if (lane == 0) {
-        uint4 s;
-        do {
-          s = hf_pkt_load(bcast + warp);
-        } while (!hf_pkt_ok(s, gen));
-        sh[HF_PW * NV + warp] = hf_pkt_val(s);
-      }
-    } else {
-      const double own = hf_warp_sum(lane < HF_PW ? sh[lane * NV + warp] : 0.0);
-      uint4 s[5];
-      bool need[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) need[k] = (lane + 32 * k) < G && (lane + 32 * k) > 0;
-      bool pending;
-      do {
-        pending = false;
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-          if (need[k]) s[k] = hf_pkt_load(set + (size_t)(lane + 32 * k) * HF_SLOT_STRIDE + warp);
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-          if (need[k]) {
-            if (hf_pkt_ok(s[k], gen)) need[k] = false;
-            else pending = true;
-          }
-      } while (pending);
-      double acc = (lane == 0) ? own : 0.0;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int j = lane + 32 * k;
-        if (j > 0 && j < G) acc += hf_pkt_val(s[k]);
-      }
-      acc = hf_warp_sum(acc);
-      if (lane == 0) {
-        hf_pkt_store(bcast + warp, acc, gen);
-        sh[HF_PW * NV + warp] = acc;
-      }
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < NV; ++i) out[i] = sh[HF_PW * NV + i];
-}
-
-#ifndef HF_RED_MODE
-#define HF_RED_MODE 1    // 0: packet slots, CTA 0 reduces and broadcasts (two L2 trips); 1: fixed-point atomics (one trip)
-#endif
 #ifndef HF_NREP
 #define HF_NREP 8        // replicated accumulator lines (spread the atomics of the G CTAs); a multiple of 8
 #endif
@@ -136,7 +60,8 @@ __device__ __forceinline__ void hf_grid_wait(double (&out)[NV], uint4* slots, in
 // last complete (kept in registers; carried from launch to launch through acc_prev).  Sets alternate
 // with the generation parity (a CTA can only add for generation g+2 after consuming g+1, which every
 // CTA contributes to only after consuming g).  A partial that is not finite or not below its bound
-// contributes a sentinel that turns the total into NaN in every CTA alike (the solve then fails loudly).
+// contributes a sentinel that turns the total into NaN and bumps the kernel's failure counter (the host then
+// repeats the run with the streaming kernel, hf_core.cu: hf_run).
 // Values of this lane's chunk (hi and lo word) when each set was last complete.  Plain scalars selected with
 // predicates: an array indexed by the generation parity ends up in local memory, and its loads and stores
 // sit on the critical path of every reduction.
@@ -195,7 +120,7 @@ __device__ __forceinline__ void hf_fx_store_state(const FxState& st, unsigned lo
 
 template <int NV>
 __device__ __forceinline__ void hf_fx_arrive(const double (&v)[NV], const int (&eb)[NV], unsigned long long* acc, unsigned gen,
-                                             double* red) {
+                                             double* red, int* fail) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
 #pragma unroll
@@ -219,9 +144,10 @@ __device__ __forceinline__ void hf_fx_arrive(const double (&v)[NV], const int (&
         hi = (long long)f;
         lo = (unsigned long long)((x - f) * 281474976710656.0);
       } else {
-        hi = 1ll << 54;                                   // sentinel: the total decodes to NaN in every CTA
+        hi = 1ll << 54;                                   // sentinel: the total decodes to NaN in (nearly) every case ...
         lo = 0ull;
-      }
+        atomicAdd(fail, 1);                               // ... and the solve is reported as failed in all of them (four
+      }                                                   // sentinels on one line add up to 2^64 = 0)
       unsigned long long* line = acc + ((size_t)(gen & 1u) * HF_NREP + (blockIdx.x % HF_NREP)) * HF_ACC_LINE + 2 * warp;
       hf_red_add(line, ((unsigned long long)hi << 8) + 1ull);
       hf_red_add(line + 1, (lo << 8) + 1ull);
@@ -232,7 +158,7 @@ __device__ __forceinline__ void hf_fx_arrive(const double (&v)[NV], const int (&
 // Warp 0 polls: lane l reads the 16-byte chunk (value l & 3, replica l >> 2).
 template <int NV>
 __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV], const unsigned long long* acc, int G, unsigned gen,
-                                           double* red, FxState& st) {
+                                           double* red, FxState& st, int* fail) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* sh = red + (gen & 1u) * (HF_PW * 3 + 3);
   if (warp == 0) {
@@ -257,8 +183,13 @@ __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV
       while (clock64() - t0 < HF_POLL_DELAY) {}
     }
 #endif
-    for (;;) {
+    bool timed_out = false;
+    for (int spins = 0;; ++spins) {
       bool ok = true;
+      if (spins > HF_SPIN_MAX) {                          // a partial never arrived: give up loudly instead of hanging
+        timed_out = true;
+        break;
+      }
 #pragma unroll
       for (int j = 0; j < HF_RPL; ++j)
         if (!okj[j]) hf_ld2(chunk[j], whi[j], wlo[j]);
@@ -295,7 +226,8 @@ __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV
 #pragma unroll
       for (int k = 1; k < NV; ++k)
         if (lane == k) e = eb[k];
-      const bool bad = shi >= (1ll << 53) || shi <= -(1ll << 53);
+      const bool bad = timed_out || shi >= (1ll << 53) || shi <= -(1ll << 53);
+      if (timed_out && lane == 0) atomicAdd(fail, 1);
       const double val = hf_scale2(fma((double)shi, 281474976710656.0, (double)slo), e - HF_FX_BITS);
       sh[HF_PW * NV + lane] = bad ? __longlong_as_double(0x7ff8000000000000ll) : val;
     }

@@ -107,15 +107,15 @@ class HeatSolver:
         _lib.check(self._L.hf_set_recycle(self._h, int(max_vectors)))
 
     def solver_path(self):
-        """1 = streaming kernel, 2 = on-chip contiguous-range kernel, 3 = on-chip patch kernel."""
+        """1 = streaming kernel (one launch per iteration), 2 = persistent streaming kernel, 3 = on-chip patch kernel."""
         rc = self._L.hf_get_solver_path(self._h)
         if rc < 0:
             _lib.check(rc)
         return rc
 
     def on_chip(self):
-        """True when the time loop runs in a persistent on-chip PCG kernel (one launch per solve)."""
-        return self.solver_path() >= 2
+        """True when the mesh fits on chip and the solves run in the on-chip patch kernel."""
+        return self.solver_path() == 3
 
     def sizes(self):
         n, nnz = C.c_int32(), C.c_int64()
@@ -184,9 +184,9 @@ class HeatSolver:
 
     def stats(self):
         """dict: device ms of the last run loop, kernels launched, PCG iterations, last relres."""
-        st = np.zeros(4)
+        st = np.zeros(5)
         _lib.check(self._L.hf_get_stats(self._h, _lib.ptr(st)))
-        return {"run_ms": st[0], "launches": int(st[1]), "iterations": int(st[2]), "relres": st[3]}
+        return {"run_ms": st[0], "launches": int(st[1]), "iterations": int(st[2]), "relres": st[3], "retries": int(st[4])}
 
     def set_sharing(self, n_concurrent):
         """Plan the on-chip kernel for ``n_concurrent`` (1 or 2) simulations sharing the GPU (call before

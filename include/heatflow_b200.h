@@ -89,8 +89,9 @@ int hf_set_source(hf_ctx* ctx, const double* s);
 
 /* solver options: rtol on ||r||_{D^-1} / ||b_free||_{D^-1}, iteration cap, warm start
  * (x0 = u_n + warm*(u_n - u_{n-1})), PCG kernels: 0 = auto (on-chip patch kernel when the mesh
- * fits, else streaming), 1 = streaming kernel (one launch per iteration), 2 = on-chip kernel with
- * contiguous ghost ranges (banded node order, <= 1.5e5 dofs), 3 = on-chip patch kernel. */
+ * fits, else the persistent streaming kernel), 1 = streaming kernel with one launch per PCG iteration
+ * (the host polls for convergence), 2 = persistent streaming kernel (one cooperative launch per solve,
+ * the iteration loop runs on the device), 3 = on-chip patch kernel. */
 int hf_set_solver(hf_ctx* ctx, double rtol, int32_t max_iters, double warm, int32_t mode);
 
 /* Initial guess from the previous time steps: keep the corrections of up to max_vectors
@@ -139,15 +140,21 @@ int hf_set_profile(hf_ctx* ctx, int32_t on);
 int hf_get_solve_profile(hf_ctx* ctx, double* solve_ms, int64_t* solve_launches);
 
 /* Which PCG kernel hf_step / hf_run will use for the current operator and hf_set_solver mode:
- * 1 = streaming kernel, 2 = on-chip kernel with contiguous ghost ranges, 3 = on-chip patch kernel
+ * 1 = streaming kernel, one launch per iteration; 2 = persistent streaming kernel; 3 = on-chip patch kernel
  * (the mesh fits in the SMs' shared memory + registers); < 0 on error. */
 int hf_get_solver_path(hf_ctx* ctx);
 
 /* Counters for benchmarking: stats[0] = device time of the step loop of the last hf_run /
  * hf_ens_run in ms (CUDA events on the context stream), stats[1] = kernels launched since
  * hf_create (graph kernel nodes included), stats[2] = PCG iterations since hf_create,
- * stats[3] = relative residual of the last solve. */
-int hf_get_stats(hf_ctx* ctx, double* stats4);
+ * stats[3] = relative residual of the last solve, stats[4] = hf_run calls that were repeated with the
+ * host-polled streaming kernel because a single-launch solve failed (iteration cap, non-finite or
+ * out-of-range partial sum; the repeat is still the GPU path - there is no CPU fallback). */
+int hf_get_stats(hf_ctx* ctx, double* stats5);
+
+/* Diagnostics for the tests: shrink the fixed-point range of the on-chip kernel's grid reduction by
+ * 2^-bits so that its overflow path (sentinel + failure counter + repeat of the run) can be exercised. */
+int hf_debug_fx_shift(hf_ctx* ctx, int32_t bits);
 
 /* r-weighted L2 projection of grad(u_n) onto vector P1, grad[N,2] = (d/dz, d/dr)
  * (reference: run_no_diamond.py:471-491, :544-550). */

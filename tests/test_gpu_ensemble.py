@@ -159,6 +159,39 @@ def test_parameter_sweep_outputs_match_oracle(tmp_path, name, factor, mode):
         assert np.abs(a[["pside", "oside"]].to_numpy() / b[["pside", "oside"]].to_numpy() - 1).max() <= 1e-11
 
 
+def test_config5_corner_variants_at_full_size_match_oracle(tmp_path):
+    # BASELINE config #5 spot check: the four corner variants (k = 1 / 100 W/m/K, fwhm = 1e-6 / 1e-4 m) of the 64 x 64
+    # sweep, on the cfg's own mesh (1.4e5 dofs) and all 100 steps, through run_parameter_sweep with its defaults -
+    # every watcher history against the LU oracle
+    import parameter_sweep as psw
+    from heatflow_b200.mesh_and_materials import read_msh
+    cfg, cfg_path = coarse_cfg_file(tmp_path, "geballe_with_diamond", 1.0)      # cfg sizes; absolute heating-file path
+    out, meshes = str(tmp_path / "sweep"), str(tmp_path / "meshes")
+    width = float(cfg["mats"]["p_sample"]["z"])
+    results, failed = psw.run_parameter_sweep(cfg_path, out, (1e-6, 1e-4), (1.0, 100.0), (width, width), (2, 2, 1),
+                                              base_mesh_folder=meshes)
+    assert failed == [] and len(results) == 4
+    nodes, tris, tag, _ = read_msh(os.path.join(psw.get_mesh_folder_for_width(meshes, width), "mesh.msh"))
+    assert len(nodes) > 130_000
+    S = int(cfg["timing"]["num_steps"])
+    dt = float(cfg["timing"]["t_final"]) / S
+    for r in results:
+        used = yaml.safe_load(open(os.path.join(out, r["run_name"], "used_config.yaml")))
+        mats, _, info = problem.stack_with_diamond(used)
+        kap = np.array([m.properties["k"] for m in mats])[tag - 1]
+        rc = np.array([m.properties["rho_cv"] for m in mats])[tag - 1]
+        zc = next(m for m in mats if m.name == "p_coupler").boundaries[0]
+        bcs = [(ho.locate_row_dofs(nodes, "left"), "const"), (ho.locate_row_dofs(nodes, "right"), "const"),
+               (ho.locate_row_dofs(nodes, "top"), "const"),
+               (ho.locate_row_dofs(nodes, "x", coord=zc, length=2 * info["r_sample"], center=0.0), "gauss")]
+        ht, hT = ho.load_heating(cfg["heating"]["file"])
+        O = ho.Oracle2D(nodes, tris, rc, kap, dt, bcs, float(used["heating"]["ic_temp"]), float(used["heating"]["fwhm"]), ht, hT)
+        watch = ho.nearest_nodes(nodes, list(psw.get_watcher_points(used).values()))
+        ohist, _ = O.run(S, watch)
+        df = pd.read_csv(os.path.join(out, r["run_name"], "watcher_points.csv"))
+        assert np.abs(df[["pside", "oside"]].to_numpy() / ohist - 1).max() <= RTOL_FIELD, r["run_name"]
+
+
 @pytest.mark.parametrize("ks,fw,cap", [
     ([1.0, 10.0, 100.0], [1e-6, 1.3e-5, 1e-4], 64),                        # padded tile, full history
     (list(np.logspace(0, 2, 16)), list(np.logspace(-6, -4, 16)[::-1]), 64),  # B = 16

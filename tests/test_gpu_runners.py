@@ -84,10 +84,14 @@ def test_run_with_diamond_outputs(tmp_path):
                                         suppress_print=True)
 
 
-def test_run_no_diamond_gradient_outputs_and_1d(tmp_path):
+@pytest.mark.parametrize("cfg_name", ["geballe_no_diamond", "geballe_1d"])
+def test_run_no_diamond_gradient_outputs_and_1d(tmp_path, cfg_name):
+    # geballe_no_diamond: BASELINE config #2 through run_no_diamond, then run_1d on its axis; geballe_1d: BASELINE
+    # config #1's own cfg (50 steps) through the same chain (reference: run_no_diamond_1d.py:166-823 needs the 2-D
+    # mesh and the radial_gradient.csv of a no-diamond run of the same cfg)
     import run_no_diamond
     import run_no_diamond_1d
-    cfg = coarse_cfg("geballe_no_diamond", 4.0)
+    cfg = coarse_cfg(cfg_name, 4.0)
     wp = sweep_watchers(cfg)
     mesh_folder, out = str(tmp_path / "mesh"), str(tmp_path / "out")
     run_no_diamond.run_simulation(cfg, mesh_folder, rebuild_mesh=True, output_folder=out, watcher_points=wp,
@@ -109,6 +113,10 @@ def test_run_no_diamond_gradient_outputs_and_1d(tmp_path):
     assert np.abs(df[["pside", "oside"]].to_numpy() / np.array(hist) - 1).max() <= 1e-10
     gd = pd.read_csv(os.path.join(out, "radial_gradient.csv"), index_col=0)
     assert gd.index.name == "time" and np.allclose(gd.columns.values.astype(float), centres, rtol=1e-14)
+    # The gradient is a DERIVED output: here the two sides project their own temperature fields, which agree to 1e-10
+    # relative (|u| ~ 2e3 K); differencing over h = 8e-8 m amplifies that to ~2e-7 K / 8e-8 m ~ 3 K/m against gradients of
+    # ~1e9 K/m, i.e. the 1e-10 bar on u bounds the gradient to ~1e-8 of its scale.  With the SAME input field the
+    # projection itself meets 1e-10 (test_gpu_parity.py::test_gradient_projection).
     scale = np.abs(np.array(rows)).max()
     assert np.abs(gd.values - np.array(rows)).max() <= 1e-8 * scale
     gr = pd.read_csv(os.path.join(out, "radial_gradient_raw.csv"), index_col=0)

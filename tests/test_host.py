@@ -196,3 +196,16 @@ def test_bench_reference_arm_under_torchrun_world_size_2():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["cores"] == 2 and d["scaling"] == "weak"
     assert "2 independent simulation" in d["config"]["workload"] and d["value"] > 0
+
+
+def test_cfgs_of_baseline_configs_1_and_2():
+    # configs[0] (geballe_1d.yaml) is the no-diamond stack with 50 steps; geballe_no_diamond_read_flux.yaml is the same
+    # file - the GPU tests run geballe_1d.yaml through run_no_diamond + run_1d (tests/test_gpu_runners.py)
+    import yaml
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    load = lambda n: yaml.safe_load(open(os.path.join(root, "cfgs", n + ".yaml")))
+    one_d, flux, nd = load("geballe_1d"), load("geballe_no_diamond_read_flux"), load("geballe_no_diamond")
+    assert one_d == flux
+    assert one_d["timing"]["num_steps"] == 50 and nd["timing"]["num_steps"] == 40
+    nd["timing"]["num_steps"] = 50
+    assert one_d == nd
