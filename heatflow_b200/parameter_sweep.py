@@ -14,7 +14,9 @@ cfg editing, :290-540 driver, :543-604 CLI).  What differs is how the runs execu
                                                  resident mesh (``mode='serial'``; ``'auto'``, the
                                                  default, picks); tiles are sharded over the GPUs
                                                  (torchrun ranks, or ``num_processes`` spawned GPU
-                                                 workers) with one final gather of the watcher histories
+                                                 workers); every rank writes the run folders of its own
+                                                 variants while its GPU works on the next ones, and one
+                                                 final gather brings the per-run summary to rank 0
   ---------------------------------------------  ---------------------------------------------
   ``mode='per_run'`` (forced by ``write_xdmf=True``) keeps the reference's behaviour of calling
   ``run_simulation`` once per parameter set, which also writes the XDMF and gradient CSV files.
@@ -29,6 +31,8 @@ import itertools
 import json
 import multiprocessing as mp
 import os
+import queue
+import threading
 import time
 from datetime import datetime
 
@@ -147,14 +151,52 @@ def get_mesh_folder_for_width(base_mesh_folder, width):
 # ----------------------------------------------------------------------------------------
 # ensemble execution of one width group
 # ----------------------------------------------------------------------------------------
-def _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine="auto"):
-    """Set the group's mesh up on ``device`` and run this rank's tiles.
-    Returns (idx, hist, iters, secs, errors, step_times)."""
+class _OutputWriter:
+    """Writes the run folders (``used_config.yaml`` + ``watcher_points.csv``, parameter_sweep.py:145-181 via
+    run_simulation) of finished variants on a host thread, so the files of one variant are written while the GPU
+    advances the next ones.  ``submit`` is the ``on_done`` callback of the sweep engine."""
+
+    def __init__(self, output_dir, base_config, combinations, step_t, names):
+        self.output_dir, self.base_config, self.combinations = output_dir, base_config, combinations
+        self.step_t, self.names = np.asarray(step_t), list(names)
+        self.errors = {}
+        self._q = queue.Queue()
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+
+    def submit(self, i, hist, iters, seconds, error):
+        if error is None:
+            self._q.put((int(i), np.array(hist, copy=True)))
+
+    def _loop(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            i, hist = item
+            try:
+                if not np.all(np.isfinite(hist)):
+                    raise FloatingPointError('non-finite watcher history')
+                _write_run_outputs(self.output_dir, self.base_config, self.combinations[i], self.step_t, hist, self.names)
+            except Exception as exc:                   # recorded per run, as the reference does
+                self.errors[i] = str(exc)
+
+    def close(self):
+        self._q.put(None)
+        self._t.join()
+        return self.errors
+
+
+def _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine="auto",
+                     output_dir=None, names=None):
+    """Set the group's mesh up on ``device``, run this rank's tiles and (``output_dir`` given) write their run
+    folders.  Returns (idx, hist, iters, secs, errors, step_times)."""
     cfg0 = modify_config_for_parameters(base_config, combinations[0]['fwhm'], combinations[0]['k'], combinations[0]['width'])
     _, stack = _runner_for(cfg0)
     with suppress_output(suppress_print):
         sim = Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device)
     extra = []
+    writer = None
     try:
         # serial engine on an on-chip mesh: two simulations share the SMs (hf_set_sharing) when the mesh
         # still fits with half the registers / shared memory per CTA
@@ -169,19 +211,39 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
         watch = sim.watcher_nodes(list(get_watcher_points(cfg0).values()))
         fwhm = np.array([c['fwhm'] for c in combinations])
         k = np.array([c['k'] for c in combinations])
-        out = sweep.run_tiles(sim, fwhm, k, tiles, watch, engine=engine, extra_sims=extra)
-        return out + (sim.step_t.copy(),)
+        if output_dir is not None:
+            writer = _OutputWriter(output_dir, base_config, combinations, sim.step_t.copy(), names)
+        idx, hist, iters, secs, errors = sweep.run_tiles(sim, fwhm, k, tiles, watch, engine=engine, extra_sims=extra,
+                                                         on_done=writer.submit if writer else None)
+        if writer is not None:
+            errors = dict(errors)
+            errors.update(writer.close())
+            writer = None
+        return idx, hist, iters, secs, errors, sim.step_t.copy()
     finally:
+        if writer is not None:
+            writer.close()
         sim.close()
         for e in extra:
             e.close()
 
 
+def _rank_share(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine, output_dir, names):
+    """``_group_on_device`` that never raises: a failure outside the per-variant handlers (set-up, out of memory)
+    marks every variant of this rank as failed, so that the rank still takes part in the final gather."""
+    mine = np.concatenate([np.asarray(t, dtype=np.int64) for t in tiles]) if len(tiles) else np.zeros(0, np.int64)
+    try:
+        idx, _hist, iters, secs, errors, _ = _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles,
+                                                            suppress_print, engine, output_dir, names)
+        return idx, iters, secs, errors
+    except Exception as exc:
+        return mine, np.full(len(mine), -1, dtype=np.int64), np.zeros(len(mine)), {int(i): str(exc) for i in mine}
+
+
 def _device_worker(args):
     """Spawned GPU worker (one per device) for sweeps launched without torchrun."""
     set_single_thread()
-    base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine = args
-    return _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine)
+    return _rank_share(*args)
 
 
 def _write_run_outputs(output_dir, base_config, combo, step_t, hist, names):
@@ -189,7 +251,7 @@ def _write_run_outputs(output_dir, base_config, combo, step_t, hist, names):
     os.makedirs(run_dir, exist_ok=True)
     config = modify_config_for_parameters(base_config, combo['fwhm'], combo['k'], combo['width'])
     with open(os.path.join(run_dir, 'used_config.yaml'), 'w') as f:
-        yaml.safe_dump(config, f)
+        yaml.dump(config, f, Dumper=getattr(yaml, 'CSafeDumper', yaml.SafeDumper))
     df = pd.DataFrame({'time': step_t})
     for w, name in enumerate(names):
         df[name] = hist[:, w]
@@ -261,6 +323,11 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
     say("Watcher points: Temperature monitoring at iridium coupler centers (pside, oside)")
     say("-" * 80)
 
+    names = list(get_watcher_points(base_config).keys())
+    # tiled modes: per-variant summaries of this rank over all width groups, gathered ONCE at the end
+    my_idx, my_iters, my_secs, my_errors = [], [], [], {}
+    group_offset, offset = [], 0
+    t_sweep = time.time()
     for width_idx, (width, combinations) in enumerate(width_groups.items()):
         say(f"\nProcessing width group {width_idx + 1}/{len(width_groups)}: width = {width:.2e} m")
         say(f"  {len(combinations)} runs for this width")
@@ -279,10 +346,11 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
             else:
                 say(f"  Reusing existing mesh for width {width:.2e} m")
         if world > 1:
+            # the other ranks wait for the mesh files of rank 0 (no data moves), then every rank loads the mesh and
+            # sets its device up concurrently
             import torch.distributed as dist
             dist.barrier()
 
-        names = list(get_watcher_points(base_config).keys())
         if mode == "per_run":
             # the reference's own scheme: one run_simulation per parameter set (this rank's share)
             mine = list(range(len(combinations)))[rank::world]
@@ -303,48 +371,50 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
 
         tiles = sweep.plan_tiles([c['k'] for c in combinations], int(batch), world if world > 1 else n_workers)
         say(f"  Starting {len(combinations)} simulations in {sum(len(t) for t in tiles)} tile(s) of <= {batch}...")
-        S = int(base_config['timing']['num_steps'])
         t_group = time.time()
         if world > 1 or n_workers == 1:
-            idx, hist, iters, secs, errors, step_t = _group_on_device(base_config, combinations, mesh_folder, batch,
-                                                                      local_rank if world > 1 else 0, tiles[rank], suppress_print,
-                                                                      mode)
-            gathered = sweep.gather_results(len(combinations), S, len(names), idx, hist, iters, secs, errors)
+            parts = [_rank_share(base_config, combinations, mesh_folder, batch, local_rank if world > 1 else 0, tiles[rank],
+                                 suppress_print, mode, output_dir, names)]
         else:
             if mp.get_start_method(allow_none=True) != 'spawn':
                 try:
                     mp.set_start_method('spawn', force=True)
                 except RuntimeError:
                     pass
-            jobs = [(base_config, combinations, mesh_folder, batch, d, tiles[d], suppress_print, mode) for d in range(n_workers)]
+            jobs = [(base_config, combinations, mesh_folder, batch, d, tiles[d], suppress_print, mode, output_dir, names)
+                    for d in range(n_workers)]
             with mp.Pool(processes=n_workers, initializer=initialize_worker) as pool:
                 parts = pool.map(_device_worker, jobs)
-            hist = np.full((len(combinations), S, len(names)), np.nan)
-            iters = np.full(len(combinations), -1, dtype=np.int64)
-            secs = np.zeros(len(combinations))
-            errors = {}
-            for idx_p, hist_p, it_p, sec_p, err_p, step_t in parts:
-                hist[idx_p], iters[idx_p], secs[idx_p] = hist_p, it_p, sec_p
-                errors.update(err_p)
-            gathered = (hist, iters, secs, errors)
-        if rank != 0:
-            total_completed += len(combinations)
-            continue
-        hist, iters, secs, errors = gathered
-        say(f"  group finished in {time.time() - t_group:.2f}s")
-        for i, combo in enumerate(combinations):
-            total_completed += 1
-            run_name = run_name_for(combo['fwhm'], combo['k'], combo['width'])
-            result = {'run_id': total_completed, 'run_name': run_name, 'fwhm': combo['fwhm'], 'k': combo['k'],
-                      'width': combo['width'], 'output_dir': os.path.join(output_dir, run_name)}
-            if i in errors or not np.all(np.isfinite(hist[i])):
-                result.update(runtime=0.0, status='failed', error=errors.get(i, 'non-finite watcher history'))
-                failed_runs.append(result)
-            else:
-                _write_run_outputs(output_dir, base_config, combo, step_t, hist[i], names)
-                result.update(runtime=float(secs[i]), status='success', error=None)
-                results.append(result)
-            _report(say, result, total_completed, len(parameter_combinations))
+        for idx_p, it_p, sec_p, err_p in parts:
+            my_idx.append(np.asarray(idx_p, dtype=np.int64) + offset)
+            my_iters.append(np.asarray(it_p, dtype=np.int64))
+            my_secs.append(np.asarray(sec_p, dtype=np.float64))
+            my_errors.update({int(i) + offset: e for i, e in err_p.items()})
+        say(f"  group finished on rank 0 in {time.time() - t_group:.2f}s")
+        group_offset.append((offset, combinations))
+        offset += len(combinations)
+
+    if mode != "per_run":
+        cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
+        gathered = sweep.gather_results(offset, 0, 0, cat(my_idx, np.int64), None, cat(my_iters, np.int64),
+                                        cat(my_secs, np.float64), my_errors)       # the single collective of the sweep
+        if rank == 0:
+            _, iters, secs, errors = gathered
+            for off, combinations in group_offset:
+                for i, combo in enumerate(combinations):
+                    total_completed += 1
+                    run_name = run_name_for(combo['fwhm'], combo['k'], combo['width'])
+                    result = {'run_id': total_completed, 'run_name': run_name, 'fwhm': combo['fwhm'], 'k': combo['k'],
+                              'width': combo['width'], 'output_dir': os.path.join(output_dir, run_name)}
+                    g = off + i
+                    if g in errors or iters[g] < 0:
+                        result.update(runtime=0.0, status='failed', error=errors.get(g, 'run did not report back'))
+                        failed_runs.append(result)
+                    else:
+                        result.update(runtime=float(secs[g]), status='success', error=None)
+                        results.append(result)
+                    _report(say, result, total_completed, len(parameter_combinations))
+            say(f"\nall groups finished in {time.time() - t_sweep:.2f}s")
 
     if rank != 0:
         return [], []

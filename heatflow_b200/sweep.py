@@ -12,8 +12,9 @@ re-factorising (parameter_sweep.py:123-192, :436-438).  Here the variants of one
     (meshes that fit on chip: the persistent kernel is latency-bound, so batching buys nothing and
     every simulation keeps the recycled-initial-guess speed-up); ``'auto'`` picks by
     ``HeatSolver.on_chip()`` - and
-  * hands its ``[P_local, S, n_watch]`` watcher histories to rank 0 in ONE final gather - the only
-    collective of the sweep.
+  * writes the run folders of its own variants while the GPU works on the next ones (``on_done``), and
+  * hands its per-variant summary (and, on request, the ``[P_local, S, n_watch]`` watcher histories) to rank 0
+    in ONE final gather - the only collective of the sweep.
 
 Sharding: variants are ordered by conductivity (similar PCG iteration counts inside a tile), cut
 into tiles of ``batch`` and dealt round-robin to the ranks, so every rank sees the same mix of
@@ -45,14 +46,15 @@ def plan_tiles(k_values, batch, world_size):
     return [cut[r::world_size] for r in range(world_size)]
 
 
-def run_tiles_serial(sims, fwhm, k, tiles, watch_nodes, sample_name="p_sample"):
+def run_tiles_serial(sims, fwhm, k, tiles, watch_nodes, sample_name="p_sample", on_done=None):
     """``run_tiles`` through the single-simulation path: same arguments, same return value
     (iters = PCG iterations of the variant itself, seconds = wall time of the variant).
 
     ``sims``: one ``Simulation2D`` or a list of them on the same device.  With two (each planned with
     ``sharing=2``) the variants are pulled from a common queue by two host threads, one context and stream
     each: the on-chip kernels of the two simulations are co-resident and hide each other's reduction
-    latency (the C calls release the GIL)."""
+    latency (the C calls release the GIL).  ``on_done(i, hist_i, iters_i, seconds_i, error_or_None)`` is called
+    from the worker thread as soon as variant ``i`` has finished."""
     import threading
     sims = list(sims) if isinstance(sims, (list, tuple)) else [sims]
     S, W = sims[0].num_steps, len(watch_nodes)
@@ -87,6 +89,8 @@ def run_tiles_serial(sims, fwhm, k, tiles, watch_nodes, sample_name="p_sample"):
                 its = -1
             with lock:
                 out[i] = (hist, its, time.time() - t0)
+            if on_done is not None:
+                on_done(i, hist, its, out[i][2], errors.get(i))
 
     if len(sims) == 1:
         worker(sims[0])
@@ -102,7 +106,7 @@ def run_tiles_serial(sims, fwhm, k, tiles, watch_nodes, sample_name="p_sample"):
             np.asarray([out[i][1] for i in todo], dtype=np.int64), np.asarray([out[i][2] for i in todo]), errors)
 
 
-def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample", engine="ensemble", extra_sims=()):
+def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample", engine="ensemble", extra_sims=(), on_done=None):
     """Advance every tile on ``sim.solver``'s device (``extra_sims``: further simulations on the same
     device for the concurrent serial engine).
 
@@ -115,7 +119,7 @@ def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample", engine="
         raise ValueError("engine must be 'auto', 'ensemble' or 'serial'")
     s = sim.solver
     if engine == "serial" or (engine == "auto" and s.on_chip()):
-        return run_tiles_serial([sim, *extra_sims], fwhm, k, tiles, watch_nodes, sample_name)
+        return run_tiles_serial([sim, *extra_sims], fwhm, k, tiles, watch_nodes, sample_name, on_done)
     S, W = sim.num_steps, len(watch_nodes)
     idx_all, hist_all, it_all, sec_all, errors = [], [], [], [], {}
     for tile in tiles:
@@ -138,6 +142,9 @@ def run_tiles(sim, fwhm, k, tiles, watch_nodes, sample_name="p_sample", engine="
             except Exception:
                 pass
         dt_tile = (time.time() - t0) / max(1, len(tile))
+        if on_done is not None:
+            for pos, i in enumerate(tile):
+                on_done(int(i), hist[pos], its, dt_tile, errors.get(int(i)))
         idx_all.append(tile)
         hist_all.append(hist)
         it_all.append(np.full(len(tile), its, dtype=np.int64))
@@ -162,46 +169,30 @@ def dist_info():
 
 
 def gather_results(n_total, S, W, idx, hist, iters, secs, errors):
-    """Final gather to rank 0.  Returns (hist [P,S,W], iters [P], secs [P], errors) on rank 0 and
-    ``None`` elsewhere.  Works on NCCL (device tensors) and gloo (CPU tensors)."""
+    """Final gather to rank 0 - ONE collective (``gather_object`` of one small dict per rank; pickled numpy arrays,
+    so it works on NCCL and gloo alike).  ``hist`` may be ``None`` when every rank has already written its own run
+    folders and rank 0 only needs the summary.  Returns (hist [P,S,W] | None, iters [P], secs [P], errors) on rank 0
+    and ``None`` elsewhere."""
     rank, world, _ = dist_info()
+    mine = {"idx": np.asarray(idx, dtype=np.int64), "iters": np.asarray(iters, dtype=np.int64),
+            "secs": np.asarray(secs, dtype=np.float64), "errors": dict(errors),
+            "hist": None if hist is None else np.ascontiguousarray(hist, dtype=np.float64).reshape(len(idx), S, W)}
     if world == 1:
-        out = np.full((n_total, S, W), np.nan)
-        it = np.full(n_total, -1, dtype=np.int64)
-        sc = np.zeros(n_total)
-        out[idx], it[idx], sc[idx] = hist, iters, secs
-        return out, it, sc, dict(errors)
-    import torch
-    import torch.distributed as dist
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    # fixed-size payload per rank: [cap, 3 + S*W] (index, iterations, seconds, history); unused rows index -1
-    cap_t = torch.tensor([len(idx)], dtype=torch.int64, device=dev)
-    dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
-    cap = int(cap_t.item())
-    pay = torch.full((cap, 3 + S * W), -1.0, dtype=torch.float64)
-    if len(idx):
-        pay[:len(idx), 0] = torch.from_numpy(idx.astype(np.float64))
-        pay[:len(idx), 1] = torch.from_numpy(iters.astype(np.float64))
-        pay[:len(idx), 2] = torch.from_numpy(np.asarray(secs, dtype=np.float64))
-        pay[:len(idx), 3:] = torch.from_numpy(np.ascontiguousarray(hist).reshape(len(idx), S * W))
-    pay = pay.to(dev)
-    bucket = [torch.empty_like(pay) for _ in range(world)] if rank == 0 else None
-    dist.gather(pay, bucket, dst=0)
-    err_list = [None] * world if rank == 0 else None
-    dist.gather_object(dict(errors), err_list, dst=0)
-    if rank != 0:
-        return None
-    out = np.full((n_total, S, W), np.nan)
+        parts = [mine]
+    else:
+        import torch.distributed as dist
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(mine, parts, dst=0)
+        if rank != 0:
+            return None
+    out = None if hist is None else np.full((n_total, S, W), np.nan)
     it = np.full(n_total, -1, dtype=np.int64)
     sc = np.zeros(n_total)
-    for t in bucket:
-        a = t.cpu().numpy()
-        a = a[a[:, 0] >= 0]
-        ii = a[:, 0].astype(np.int64)
-        out[ii] = a[:, 3:].reshape(len(ii), S, W)
-        it[ii] = a[:, 1].astype(np.int64)
-        sc[ii] = a[:, 2]
     merged = {}
-    for e in err_list:
-        merged.update(e)
+    for part in parts:
+        ii = part["idx"]
+        if out is not None and part["hist"] is not None:
+            out[ii] = part["hist"]
+        it[ii], sc[ii] = part["iters"], part["secs"]
+        merged.update(part["errors"])
     return out, it, sc, merged

@@ -358,7 +358,7 @@ def test_konopkova_1m_dofs_vs_lu_oracle_every_step(konopkova_1m):
     for k in range(S):
         uo = O.step((first + k + 1) * c.dt)
         assert np.abs(fields[k] / uo - 1).max() <= RTOL_FIELD, k
-    assert np.abs(uo - c.ic).max() > 100.0
+    assert np.abs(uo - c.ic).max() > 10.0                     # a heated state, not the trivial one
     s.set_solver(rtol=1e-14, warm=0.0, mode=1)
     s.set_recycle(0)
     s.set_state(u_before_last)

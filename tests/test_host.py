@@ -195,7 +195,7 @@ def test_bench_reference_arm_under_torchrun_world_size_2():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["cores"] == 2 and d["scaling"] == "weak"
-    assert "2 independent simulation" in d["config"]["workload"] and d["value"] > 0
+    assert "2 independent cop" in d["config"]["workload"] and d["value"] > 0 and d["warmup"] == 3
 
 
 def test_cfgs_of_baseline_configs_1_and_2():
