@@ -515,8 +515,11 @@ int hf_build_patches(const hf_ctx* c, int R, std::vector<int>& halo_ptr, std::ve
 // values of an operator whose structure (slices, patches, local columns, plans) is already on the device
 static int sell_fill_values(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out) {
   if (val_bc_out && val_bc_out->n != (size_t)c->nnz) HF_TRY(val_bc_out->alloc(c->nnz, c->stream));
-  DevBuf<int> bad;
-  HF_TRY(bad.alloc(1, c->stream));
+  // scratch kept in the context: a temporary released with cudaFree would synchronise the whole device and stall on
+  // the other context's queued solves when two simulations share the GPU (hf_set_sharing)
+  DevBuf<int>& bad = c->sc_flag;
+  if (bad.n != 1) HF_TRY(bad.alloc(1, c->stream));
+  HF_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), c->stream));
   const int g = (c->Npad + 255) / 256;
   k_diag_scale<<<g, 256, 0, c->stream>>>(c->N, c->Npad, c->rowptr.p, c->col.p, csr_val.p, c->bcflag.p, apply_bc ? 1 : 0,
                                          op.scale.p, bad.p);
@@ -598,12 +601,13 @@ int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellO
 static int cell_coefs(hf_ctx* c, double fm, double fk) {
   const int nt = (int)c->mat_tags.size();
   if (nt == 0) return hf_fail(HF_ERR_STATE, "call hf_set_materials first");
-  DevBuf<int> tags, miss;
-  DevBuf<double> kap, rc;
+  DevBuf<int>&tags = c->sc_tags, &miss = c->sc_flag;      // context scratch: no cudaFree (device-wide sync) per call
+  DevBuf<double>&kap = c->sc_kap, &rc = c->sc_rc;
   HF_TRY(tags.upload(c->mat_tags.data(), nt, c->stream));
   HF_TRY(kap.upload(c->mat_kappa.data(), nt, c->stream));
   HF_TRY(rc.upload(c->mat_rhoc.data(), nt, c->stream));
-  HF_TRY(miss.alloc(1, c->stream));
+  if (miss.n != 1) HF_TRY(miss.alloc(1, c->stream));
+  HF_CUDA(cudaMemsetAsync(miss.p, 0, sizeof(int), c->stream));
   k_cell_coef<<<(c->E + 255) / 256, 256, 0, c->stream>>>(c->E, c->cell_tag.p, nt, tags.p, kap.p, rc.p, fm, fk, c->cm.p,
                                                          c->ck.p, miss.p);
   int hm = 0;
@@ -741,7 +745,7 @@ extern "C" int hf_set_source(hf_ctx* c, const double* s) {
 
 extern "C" int hf_set_solver(hf_ctx* c, double rtol, int32_t max_iters, double warm, int32_t mode) {
   if (!c) return hf_fail(HF_ERR_ARG, "null context");
-  if (!(rtol > 0.0) || max_iters <= 0 || mode < 0 || mode > 3) return hf_fail(HF_ERR_ARG, "hf_set_solver: bad arguments");
+  if (!(rtol > 0.0) || max_iters <= 0 || mode < 0 || mode > 4) return hf_fail(HF_ERR_ARG, "hf_set_solver: bad arguments");
   c->rtol = rtol;
   c->max_iters = max_iters;
   c->warm = warm;
@@ -833,23 +837,24 @@ __global__ void k_sample(int n, const int* __restrict__ nodes, const double* __r
   if (i < n) out[i] = u[nodes[i]];
 }
 
-// Which PCG kernel solves with `op` (hf_get_solver_path): 1 = streaming kernel, one launch per iteration, the host
-// polls (k_pcg_iter); 2 = persistent streaming kernel, one cooperative launch per solve (k_pcg_stream); 3 = on-chip
-// patch kernel, one cooperative launch per solve (k_pcg_patch).  Paths 2 and 3 are fully asynchronous.
+// Which PCG kernel solves with `op`: 1 = streaming kernel, one launch per iteration, the host polls (k_pcg_iter);
+// 2 = persistent streaming kernel, one cooperative launch per solve (k_pcg_stream); 3 = on-chip patch kernel, one
+// cooperative launch per solve (k_pcg_patch, or its pipelined variant k_pcg_pipe, which hf_get_solver_path reports
+// as 4).  Paths 2 and 3 are fully asynchronous.
 static bool has_patch_plan(const SellOp& op) { return op.pp_rpt != 0 || (op.plan_from && op.plan_from->pp_rpt != 0); }
 
 static int pick_path(hf_ctx* c, const SellOp& op, int* path) {
   const int mode = c->force_mode >= 0 ? c->force_mode : c->mode;
   // a specific single-launch kernel was requested: plan it on demand
-  if (mode == 3 && !has_patch_plan(op)) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));
-  if (mode == 3 && !has_patch_plan(op))
-    return hf_fail(HF_ERR_STATE, "the on-chip PCG kernel was requested (solver mode 3) but the mesh does not fit on chip");
+  if (mode >= 3 && !has_patch_plan(op)) HF_TRY(hf_patch_plan(c, const_cast<SellOp&>(op)));
+  if (mode >= 3 && !has_patch_plan(op))
+    return hf_fail(HF_ERR_STATE, "the on-chip PCG kernel was requested (solver mode 3 / 4) but the mesh does not fit on chip");
   if ((mode == 2 || (mode == 0 && !has_patch_plan(op))) && !op.st_grid) HF_TRY(hf_stream_plan(c, const_cast<SellOp&>(op)));
   if (mode == 2 && !op.st_grid)
     return hf_fail(HF_ERR_STATE, "the persistent streaming PCG kernel was requested (solver mode 2) but cannot be launched "
                                  "cooperatively on this device");
   if (mode == 0) *path = has_patch_plan(op) ? 3 : (op.st_grid ? 2 : 1);
-  else *path = mode;
+  else *path = mode >= 3 ? 3 : mode;
   return HF_OK;
 }
 
@@ -1083,7 +1088,7 @@ extern "C" int hf_get_solver_path(hf_ctx* c) {
   if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_get_solver_path: operator not built");
   int path = 1;
   HF_TRY(pick_path(c, c->opA, &path));
-  return path;
+  return (path == 3 && hf_patch_pipelined(c, c->opA)) ? 4 : path;
 }
 
 extern "C" int hf_get_stats(hf_ctx* c, double* st) {

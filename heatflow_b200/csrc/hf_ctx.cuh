@@ -196,6 +196,8 @@ struct hf_ctx {
   std::vector<int> mat_tags;
   std::vector<double> mat_kappa, mat_rhoc;
   DevBuf<double> cm, ck;               // per-cell coefficients fed to the assembly kernel
+  DevBuf<int> sc_tags, sc_flag;        // set-up scratch (material table, error flag), reused across calls
+  DevBuf<double> sc_kap, sc_rc;
   // boundary conditions
   int n_bc = 0, n_gauss = 0;
   DevBuf<int> bc_dofs, gauss_dof;
@@ -293,6 +295,7 @@ int hf_patch_plan(hf_ctx* c, SellOp& op);
 int hf_stream_plan(hf_ctx* c, SellOp& op);
 int hf_stream_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts = false);
 int hf_patch_solve_async(hf_ctx* c, const SellOp& op, int step_slot, bool sum_parts = false);
+bool hf_patch_pipelined(const hf_ctx* c, const SellOp& op);
 int hf_build_sell(hf_ctx* c, const DevBuf<double>& csr_val, bool apply_bc, SellOp& op, DevBuf<double>* val_bc_out);
 int hf_assemble_values(hf_ctx* c, const double* cm, const double* ck, int axisym, double* out);
 void hf_ens_free(hf_ctx* c);

@@ -35,9 +35,10 @@ class XDMFFile:
         self.data_dir = f"{self.stem}_data"
         os.makedirs(os.path.join(self.folder, self.data_dir), exist_ok=True)
         self._mesh_xml = None
-        self._series = {}       # function name -> list of (time, relative file)
+        self._series = {}       # function name -> [relative heavy-data file, list of per-step grid XML, bytes written]
         self._n_nodes = 0
         self._closed = False
+        self._unflushed = 0
 
     def _dump(self, rel, array):
         array.tofile(os.path.join(self.folder, rel))
@@ -64,41 +65,54 @@ class XDMFFile:
             f'    </Grid>\n')
         self._flush()
 
+    FLUSH_EVERY = 32            # the light-data XML is rewritten every this many steps and on close()
+
     def write_function(self, u, t=0.0):
-        """``u``: object with ``.name`` and ``.x.array`` (nodal values), like a dolfinx Function."""
+        """``u``: object with ``.name`` and ``.x.array`` (nodal values), like a dolfinx Function.  The values are
+        appended to ONE heavy-data file per function (``Seek`` offsets in the DataItems) and the per-step grid text
+        is built once, so a run of S steps costs O(S) host work; the XML is complete after ``close()`` (and after
+        every ``FLUSH_EVERY`` steps, so that an interrupted run leaves a readable file)."""
         if self._mesh_xml is None:
             raise RuntimeError("write_mesh must be called before write_function")
         values = np.ascontiguousarray(u.x.array[: self._n_nodes], dtype="<f8")
         name = getattr(u, "name", "f")
-        series = self._series.setdefault(name, [])
-        rel = f"{self.data_dir}/{_safe(name)}_{len(series):06d}.bin"
-        self._dump(rel, values)
-        series.append((float(t), rel))
-        self._flush()
+        if name not in self._series:
+            rel = f"{self.data_dir}/{_safe(name)}.bin"
+            open(os.path.join(self.folder, rel), "wb").close()
+            self._series[name] = [rel, [], 0]
+        entry = self._series[name]
+        rel, grids, offset = entry
+        with open(os.path.join(self.folder, rel), "ab") as f:
+            values.tofile(f)
+        q = quoteattr(name)
+        grids.append(
+            f'      <Grid Name={q} GridType="Uniform">\n'
+            f'        <xi:include xpointer="xpointer(/Xdmf/Domain/Grid[@GridType=\'Uniform\'][1]/*[self::Topology or self::Geometry])" />\n'
+            f'        <Time Value="{float(t)!r}" />\n'
+            f'        <Attribute Name={q} AttributeType="Scalar" Center="Node">\n'
+            f'          <DataItem Dimensions="{self._n_nodes} 1" NumberType="Float" Precision="8" '
+            f'Format="Binary" Endian="Little" Seek="{offset}">{rel}</DataItem>\n'
+            f'        </Attribute>\n'
+            f'      </Grid>\n')
+        entry[2] = offset + values.nbytes
+        self._unflushed += 1
+        if self._unflushed >= self.FLUSH_EVERY or sum(len(e[1]) for e in self._series.values()) == 1:
+            self._flush()
 
     def _flush(self):
         out = ['<?xml version="1.0"?>\n<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>\n'
                '<Xdmf Version="3.0" xmlns:xi="https://www.w3.org/2001/XInclude">\n  <Domain>\n']
         out.append(self._mesh_xml or "")
-        for name, series in self._series.items():
-            q = quoteattr(name)
-            out.append(f'    <Grid Name={q} GridType="Collection" CollectionType="Temporal">\n')
-            for t, rel in series:
-                out.append(
-                    f'      <Grid Name={q} GridType="Uniform">\n'
-                    f'        <xi:include xpointer="xpointer(/Xdmf/Domain/Grid[@GridType=\'Uniform\'][1]/*[self::Topology or self::Geometry])" />\n'
-                    f'        <Time Value="{t!r}" />\n'
-                    f'        <Attribute Name={q} AttributeType="Scalar" Center="Node">\n'
-                    f'          <DataItem Dimensions="{self._n_nodes} 1" NumberType="Float" Precision="8" '
-                    f'Format="Binary" Endian="Little">{rel}</DataItem>\n'
-                    f'        </Attribute>\n'
-                    f'      </Grid>\n')
+        for name, (_rel, grids, _n) in self._series.items():
+            out.append(f'    <Grid Name={quoteattr(name)} GridType="Collection" CollectionType="Temporal">\n')
+            out.extend(grids)
             out.append('    </Grid>\n')
         out.append('  </Domain>\n</Xdmf>\n')
         tmp = self.path + ".tmp"
         with open(tmp, "w") as f:
             f.write("".join(out))
         os.replace(tmp, self.path)
+        self._unflushed = 0
 
     def close(self):
         if not self._closed:

@@ -204,7 +204,7 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
         if engine in ("auto", "serial") and n_mine > 1 and sim.solver.on_chip():
             with suppress_output(suppress_print):
                 sim.set_sharing(2)
-                if sim.solver.solver_path() == 3:
+                if sim.solver.on_chip():
                     extra.append(Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device, sharing=2))
                 else:
                     sim.set_sharing(1)

@@ -107,7 +107,8 @@ class HeatSolver:
         _lib.check(self._L.hf_set_recycle(self._h, int(max_vectors)))
 
     def solver_path(self):
-        """1 = streaming kernel (one launch per iteration), 2 = persistent streaming kernel, 3 = on-chip patch kernel."""
+        """1 = streaming kernel (one launch per iteration), 2 = persistent streaming kernel, 3 = on-chip patch kernel
+        (classic CG), 4 = on-chip patch kernel (pipelined CG)."""
         rc = self._L.hf_get_solver_path(self._h)
         if rc < 0:
             _lib.check(rc)
@@ -115,7 +116,7 @@ class HeatSolver:
 
     def on_chip(self):
         """True when the mesh fits on chip and the solves run in the on-chip patch kernel."""
-        return self.solver_path() == 3
+        return self.solver_path() >= 3
 
     def sizes(self):
         n, nnz = C.c_int32(), C.c_int64()

@@ -116,7 +116,13 @@ class Space:
         s = self._solver
         if self._built != sig:
             xy = np.array(self.mesh.geometry.x[:, :2], dtype=np.float64)
-            xy[:, 1] = np.abs(xy[:, 1] - r0)                    # r = sqrt((x[1] - r0)^2), space_and_forms.py:99
+            # r = sqrt((x[1] - r0)^2), space_and_forms.py:99.  The weight is applied by shifting / mirroring the radial
+            # coordinate, which leaves every triangle's shape intact only when r0 is not strictly inside the mesh (a
+            # triangle straddling r0 would be folded: wrong area and gradients, not just a wrong weight)
+            if axisym and xy[:, 1].min() < r0 < xy[:, 1].max():
+                raise ValueError(f"Space: r0 = {r0} lies strictly inside the radial extent of the mesh "
+                                 f"[{xy[:, 1].min()}, {xy[:, 1].max()}]; the r-weighted forms need r0 at or outside an edge")
+            xy[:, 1] = np.abs(xy[:, 1] - r0)
             pairs, tag = np.unique(np.stack([kap, rc], axis=1), axis=0, return_inverse=True)
             s.set_mesh(xy, self.mesh.cells, (tag.reshape(-1) + 1).astype(np.int32))
             s.set_materials(np.arange(1, len(pairs) + 1, dtype=np.int32), pairs[:, 0], pairs[:, 1])

@@ -91,7 +91,8 @@ int hf_set_source(hf_ctx* ctx, const double* s);
  * (x0 = u_n + warm*(u_n - u_{n-1})), PCG kernels: 0 = auto (on-chip patch kernel when the mesh
  * fits, else the persistent streaming kernel), 1 = streaming kernel with one launch per PCG iteration
  * (the host polls for convergence), 2 = persistent streaming kernel (one cooperative launch per solve,
- * the iteration loop runs on the device), 3 = on-chip patch kernel. */
+ * the iteration loop runs on the device), 3 = on-chip patch kernel (pipelined CG variant when the mesh
+ * leaves room for its extra vectors, <= 6 rows per thread), 4 = on-chip patch kernel, classic CG only. */
 int hf_set_solver(hf_ctx* ctx, double rtol, int32_t max_iters, double warm, int32_t mode);
 
 /* Initial guess from the previous time steps: keep the corrections of up to max_vectors
@@ -141,7 +142,8 @@ int hf_get_solve_profile(hf_ctx* ctx, double* solve_ms, int64_t* solve_launches)
 
 /* Which PCG kernel hf_step / hf_run will use for the current operator and hf_set_solver mode:
  * 1 = streaming kernel, one launch per iteration; 2 = persistent streaming kernel; 3 = on-chip patch kernel
- * (the mesh fits in the SMs' shared memory + registers); < 0 on error. */
+ * (the mesh fits in the SMs' shared memory + registers), classic CG; 4 = on-chip patch kernel, pipelined CG
+ * (the grid reduction overlaps the SpMV); < 0 on error. */
 int hf_get_solver_path(hf_ctx* ctx);
 
 /* Counters for benchmarking: stats[0] = device time of the step loop of the last hf_run /

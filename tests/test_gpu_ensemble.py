@@ -231,7 +231,7 @@ def test_two_simulations_sharing_the_gpu_match_sequential_runs(wd):
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 3e-8, 0.0), (0.95e-6, 0.0)])
     fws = [2e-6, 7e-6, 1.3e-5, 4e-5, 9e-5, 3e-6]
     ref = make_solver(c, warm=1.0, recycle=64)
-    assert ref.solver_path() == 3
+    assert ref.on_chip()
     alone = []
     for f in fws:
         ref.set_state(np.full(len(c.nodes), c.ic))
@@ -249,7 +249,7 @@ def test_two_simulations_sharing_the_gpu_match_sequential_runs(wd):
         s.build_operator(c.dt, True)
         s.set_solver(rtol=1e-14, warm=1.0)
         s.set_recycle(64)
-        assert s.solver_path() == 3
+        assert s.on_chip()
         pair.append(s)
     got = {}
 

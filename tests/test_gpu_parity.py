@@ -15,9 +15,10 @@ pytestmark = pytest.mark.gpu
 
 RTOL_FIELD = 1e-10   # the tolerance north_star states for temperature histories
 # solver modes (hf_set_solver): 1 = streaming kernel, one launch per PCG iteration; 2 = persistent streaming kernel,
-# one cooperative launch per solve; 3 = on-chip patch kernel (meant for Hilbert-ordered meshes, the default)
-ORDERING = {0: "auto", 1: "auto", 2: "auto", 3: "hilbert"}
-MODES = pytest.mark.parametrize("mode", [1, 2, 3], ids=["streaming", "stream-persistent", "patch"])
+# one cooperative launch per solve; 3 = on-chip patch kernel (pipelined CG where the mesh leaves room for it; meant for
+# Hilbert-ordered meshes, the default); 4 = on-chip patch kernel, classic CG
+ORDERING = {0: "auto", 1: "auto", 2: "auto", 3: "hilbert", 4: "hilbert"}
+MODES = pytest.mark.parametrize("mode", [1, 2, 3, 4], ids=["streaming", "stream-persistent", "patch-pipelined", "patch-classic"])
 
 
 def rel_err(a, b):
@@ -325,7 +326,7 @@ def test_headline_config_full_size_all_steps_runner_defaults():
     # fields at EVERY step against the LU oracle
     c = build_case("geballe_with_diamond", 1.0)
     s = make_solver(c, warm=1.0, recycle=128)
-    assert s.solver_path() == 3
+    assert s.on_chip()
     O = make_oracle(c)
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
     hist, iters, fields = s.run(c.amps, c.ic, c.coeff, watch, keep_fields=True)

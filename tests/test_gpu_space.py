@@ -53,6 +53,10 @@ def test_transient_step_matches_oracle_and_reference_api(nd):
         it, rel = sp_.step([bc.bc for bc in bcs])                       # fem.dirichletbc stand-ins work too
         ou = O.step(t)
         assert it > 0 and np.abs(u_n.x.array / ou - 1).max() <= 1e-10
+    # an axis r0 strictly inside the mesh would fold the triangles that straddle it: refused, not silently wrong
+    sp_.build_variational_forms(rho_c, kappa, u_n, c.dt, 0.5 * c.nodes[:, 1].max())
+    with pytest.raises(ValueError, match="r0"):
+        sp_.assemble_matrix(bcs)
     sp_.close()
 
 
