@@ -48,6 +48,7 @@ SIGNATURES = {
     "hf_sample": (C.c_int, [_vp, _i32, _vp, _vp]),
     "hf_get_stats": (C.c_int, [_vp, _vp]),
     "hf_debug_fx_shift": (C.c_int, [_vp, _i32]),
+    "hf_debug_phase_times": (C.c_int, [_vp, _vp, _i32]),
     "hf_project_gradient": (C.c_int, [_vp, _vp, C.POINTER(_i32)]),
     "hf_spmv": (C.c_int, [_vp, _vp, _vp]),
     "hf_bench_kernels": (C.c_int, [_vp, _i32, _i32, _vp]),

@@ -1101,6 +1101,20 @@ extern "C" int hf_get_stats(hf_ctx* c, double* st) {
   return HF_OK;
 }
 
+// Diagnostics: per-CTA clock64 cycles spent in the phases of the pipelined on-chip kernel during the last solve
+// ([grid][2 warps][8 phases]; all zero unless the library was built with -DHF_PHASE_TIMING).  n = 0 switches it off.
+extern "C" int hf_debug_phase_times(hf_ctx* c, int64_t* out, int32_t n) {
+  if (!c || n < 0) return hf_fail(HF_ERR_ARG, "hf_debug_phase_times: bad arguments");
+  cudaSetDevice(c->device);
+  if (n == 0) {
+    c->debug_phase.release();
+    return HF_OK;
+  }
+  if (c->debug_phase.n != (size_t)n) return c->debug_phase.alloc(n, c->stream);     // first call: arm
+  if (!out) return hf_fail(HF_ERR_ARG, "hf_debug_phase_times: null output");
+  return c->debug_phase.download(reinterpret_cast<long long*>(out), n, c->stream);
+}
+
 extern "C" int hf_debug_fx_shift(hf_ctx* c, int32_t bits) {
   if (!c || bits < 0 || bits > 400) return hf_fail(HF_ERR_ARG, "hf_debug_fx_shift: bits must be in [0, 400]");
   c->debug_fx_shift = bits;

@@ -222,6 +222,7 @@ struct hf_ctx {
   int share = 1;                       // hf_set_sharing: solves expected to run concurrently on this device (1 or 2)
   int max_iters = 20000, mode = 0, last_iters = 0;
   int debug_fx_shift = 0;              // hf_debug_fx_shift (tests): shrinks the fixed-point range of the on-chip reduction
+  DevBuf<long long> debug_phase;       // hf_debug_phase_times: per-CTA phase clocks of the last on-chip solve
   int force_mode = -1;                 // >= 0: overrides `mode` (the retry of a failed single-launch run)
   unsigned long long stat_retries = 0; // runs repeated with the host-polled kernel after a failed single-launch solve
   DevBuf<double> u0_keep;              // [2N] u, uprev at the start of hf_run

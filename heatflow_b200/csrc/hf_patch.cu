@@ -38,7 +38,25 @@ struct PatchArgs {
   double rtol;
   int mat_cap, halo_cap;
   int eb_shift;                  // diagnostics (hf_debug_fx_shift): subtracted from the fixed-point exponent bounds
+  long long* phase;              // diagnostics (-DHF_PHASE_TIMING): [G][2][8] clock64 cycles per phase, warps 0 and 1
 };
+
+#ifdef HF_PHASE_TIMING
+#define HF_PT_DECL long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t0 = clock64();
+#define HF_PT_MARK(i)                                   \
+  do {                                                  \
+    const long long t1__ = clock64();                   \
+    pt_acc[i] += t1__ - pt_t0;                          \
+    pt_t0 = t1__;                                       \
+  } while (0)
+#define HF_PT_STORE                                                                         \
+  if (P.phase && lane == 0 && warp < 2)                                                     \
+    for (int i__ = 0; i__ < 8; ++i__) P.phase[((size_t)blockIdx.x * 2 + warp) * 8 + i__] = pt_acc[i__];
+#else
+#define HF_PT_DECL
+#define HF_PT_MARK(i)
+#define HF_PT_STORE
+#endif
 
 // MINB = CTAs per SM the kernel is compiled for.  1: the whole register file of the SM caches operator rows
 // (fastest single solve).  2: half the registers and at most half the shared memory, so that the cooperative
@@ -305,7 +323,10 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_patch(PatchArgs P) {
 //     beta = gamma_i / gamma_{i-1} ; alpha = gamma_i / (delta_i - beta gamma_i / alpha_{i-1})      <- wait
 //     z = q + beta z ; s = w + beta s ; p = r + beta p ; x += alpha p ; r -= alpha s ; w -= alpha z
 // Same Krylov iterates as classic CG in exact arithmetic; the stopping test is on gamma, the directly summed
-// ||r||^2 of the iterate x holds.  Measured against the LU oracle on the benchmark operators (numpy prototype,
+// ||r||^2 of the iterate x holds.  Measured (clock64 per phase, N = 1.4e5, 138 CTAs, cycles per iteration): arrive
+// 1000, SpMV 940, halo fetch 1440 (hidden), wait for the sum 530 after the fetch, update 575: 2.42 us per iteration
+// against 2.56 us for the classic kernel - the reduction trip (~2900 cycles from arrival to result) is now the
+// critical path by itself; with 6 rows per thread the smaller register cache costs more than the overlap gains.  Measured against the LU oracle on the benchmark operators (numpy prototype,
 // 3 sweep corner variants x 100 steps): same iteration counts (+-1 %) and the same 1e-12 .. 1.5e-11 agreement
 // as classic CG - no residual replacement needed at rtol 1e-14.  Per row the CTA keeps x r p s z w in
 // registers (own rows), w on own + halo rows and z on halo rows in shared memory.
@@ -482,7 +503,7 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_pipe(PatchArgs P) {
 
   int it = 0;
   bool done = !(rr > thr);
-  double gam_old = 1.0, alpha = 1.0, gam_est = rr;
+  double inv_gam_old = 1.0, inv_alpha = 1.0, alpha = 1.0, gam_est = rr;
   FxState fx;
   hf_fx_load_state(fx, P.acc_prev);
   if (!done && P.max_it > 0) {
@@ -496,8 +517,10 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_pipe(PatchArgs P) {
     for (int h = tid; h < nh; h += HF_PT) sw[R + h] = sqh[h];
     __syncthreads();
   }
+  HF_PT_DECL
   while (!done && it < P.max_it) {
     ++gen;
+    HF_PT_MARK(7);
     // ---- gamma = r.r, delta = w.r on the own rows: the reduction starts before the SpMV
     double d[2] = {0.0, 0.0};
 #pragma unroll
@@ -508,25 +531,29 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_pipe(PatchArgs P) {
     const int e_g = hf_exp2(gam_est);
     const int eb2[2] = {hf_clamp_exp(e_g + HF_FX_MARGIN - P.eb_shift), hf_clamp_exp(e_g + 4 + HF_FX_MARGIN)};
     hf_fx_arrive<2>(d, eb2, P.acc, gen, red, P.fail);
+    HF_PT_MARK(0);
     // ---- q = Ahat w while the reduction is in flight; halo q packets
     double q[RPT];
     spmv(q);
+    HF_PT_MARK(1);
     exchange(q, it & 1, gen, sqh, true);
+    HF_PT_MARK(2);
     double tot[2];
-    hf_fx_wait<2>(tot, eb2, P.acc, G, gen, red, fx, P.fail);
+    hf_fx_wait<2, 0>(tot, eb2, P.acc, G, gen, red, fx, P.fail);   // no poll delay: the SpMV has already covered the trip
+    HF_PT_MARK(3);
     const double gam = tot[0], delta = tot[1];
     rr = gam;
     if (!(gam > thr)) {                            // also stops on NaN; x is the iterate gamma belongs to
       done = true;
       break;
     }
-    double beta = 0.0;
-    if (it > 0) {
-      beta = gam / gam_old;
-      alpha = gam / (delta - beta * gam / alpha);
-    } else {
-      alpha = gam / delta;
-    }
+    // beta = gamma_i / gamma_{i-1}, alpha = gamma_i / (delta_i - beta gamma_i / alpha_{i-1}) with the reciprocals of
+    // gamma_{i-1} and alpha_{i-1} carried over: one division on the critical path (two independent ones per iteration)
+    const double beta = (it > 0) ? gam * inv_gam_old : 0.0;
+    const double den = (it > 0) ? fma(-beta * gam, inv_alpha, delta) : delta;
+    alpha = gam / den;
+    inv_alpha = den / gam;
+    inv_gam_old = 1.0 / gam;
     // ---- own rows: z = q + beta z ; s = w + beta s ; p = r + beta p ; x += alpha p ; r -= alpha s ; w -= alpha z
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
@@ -546,11 +573,13 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_pipe(PatchArgs P) {
       szh[h] = zh;
       sw[R + h] = fma(-alpha, zh, sw[R + h]);
     }
-    gam_old = gam;
     gam_est = gam;
     ++it;
+    HF_PT_MARK(4);
     __syncthreads();
+    HF_PT_MARK(5);
   }
+  HF_PT_STORE
 #pragma unroll
   for (int k = 0; k < RPT; ++k)
     if (wid[k] >= 0) P.x[lo + (warp * RPT + k) * 32 + lane] = x[k];
@@ -595,7 +624,7 @@ static const int kPatchRpt[6] = {4, 6, 8, 10, 12, 14};
 static const int kPatchK[2][6] = {{8, 6, 4, 4, 3, 2}, {2, 1, 0, 0, 0, 0}};   // [share - 1][rows-per-thread index]
 // the pipelined variant keeps six vectors of the own rows in registers, so it caches fewer operator entries (-1: no such
 // kernel); the shared-memory operator part is sized for the smaller of the two caches
-static const int kPipeK[2][6] = {{8, 4, -1, -1, -1, -1}, {1, -1, -1, -1, -1, -1}};
+static const int kPipeK[2][6] = {{8, -1, -1, -1, -1, -1}, {1, -1, -1, -1, -1, -1}};
 
 static const void* patch_kernel(int rpt, int share) {
   if (share == 2) {
@@ -626,8 +655,7 @@ static const void* pipe_kernel(int rpt, int share) {
     }
   }
   switch (rpt) {
-    case 4: return (const void*)k_pcg_pipe<4, 8, 1>;
-    case 6: return (const void*)k_pcg_pipe<6, 4, 1>;
+    case 4: return (const void*)k_pcg_pipe<4, 8, 1>;       // rpt 6 (K = 4) measured 2 % slower than the classic kernel
     default: return nullptr;
   }
 }
@@ -743,6 +771,7 @@ int hf_patch_solve_async(hf_ctx* c, const SellOp& vals, int step_slot, bool sum_
   a.mat_cap = op.pp_mat_cap;
   a.halo_cap = op.pp_halo_cap;
   a.eb_shift = c->debug_fx_shift;
+  a.phase = c->debug_phase.n ? c->debug_phase.p : nullptr;
   void* args[] = {&a};
   const void* fn = hf_patch_pipelined(c, vals) ? pipe_kernel(op.pp_rpt, op.pp_share) : patch_kernel(op.pp_rpt, op.pp_share);
   HF_TRY(patch_set_smem_rpt(op.pp_rpt, op.pp_share, op.pp_smem));   // per function, not per operator

@@ -156,7 +156,7 @@ __device__ __forceinline__ void hf_fx_arrive(const double (&v)[NV], const int (&
 }
 
 // Warp 0 polls: lane l reads the 16-byte chunk (value l & 3, replica l >> 2).
-template <int NV>
+template <int NV, int DELAY = HF_POLL_DELAY>
 __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV], const unsigned long long* acc, int G, unsigned gen,
                                            double* red, FxState& st, int* fail) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -177,12 +177,10 @@ __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV
       plo[j] = set ? st.lo1[j] : st.lo0[j];
       whi[j] = wlo[j] = 0ull;
     }
-#if HF_POLL_DELAY
-    {                                                     // the sum cannot be complete sooner than one trip through L2
+    if (DELAY > 0) {                                      // the sum cannot be complete sooner than one trip through L2
       const long long t0 = clock64();
-      while (clock64() - t0 < HF_POLL_DELAY) {}
+      while (clock64() - t0 < DELAY) {}
     }
-#endif
     bool timed_out = false;
     for (int spins = 0;; ++spins) {
       bool ok = true;

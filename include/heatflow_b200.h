@@ -92,7 +92,7 @@ int hf_set_source(hf_ctx* ctx, const double* s);
  * fits, else the persistent streaming kernel), 1 = streaming kernel with one launch per PCG iteration
  * (the host polls for convergence), 2 = persistent streaming kernel (one cooperative launch per solve,
  * the iteration loop runs on the device), 3 = on-chip patch kernel (pipelined CG variant when the mesh
- * leaves room for its extra vectors, <= 6 rows per thread), 4 = on-chip patch kernel, classic CG only. */
+ * is small enough for its six register-resident vectors per row: <= 148 x 1024 dofs), 4 = on-chip patch kernel, classic CG only. */
 int hf_set_solver(hf_ctx* ctx, double rtol, int32_t max_iters, double warm, int32_t mode);
 
 /* Initial guess from the previous time steps: keep the corrections of up to max_vectors
@@ -157,6 +157,10 @@ int hf_get_stats(hf_ctx* ctx, double* stats5);
 /* Diagnostics for the tests: shrink the fixed-point range of the on-chip kernel's grid reduction by
  * 2^-bits so that its overflow path (sentinel + failure counter + repeat of the run) can be exercised. */
 int hf_debug_fx_shift(hf_ctx* ctx, int32_t bits);
+
+/* Diagnostics (profiling builds, -DHF_PHASE_TIMING): clock64 cycles per phase of the pipelined on-chip kernel in
+ * the last solve, out[grid][2][8].  The first call with a new n arms the buffer, later calls read it; n = 0 disarms. */
+int hf_debug_phase_times(hf_ctx* ctx, int64_t* out, int32_t n);
 
 /* r-weighted L2 projection of grad(u_n) onto vector P1, grad[N,2] = (d/dz, d/dr)
  * (reference: run_no_diamond.py:471-491, :544-550). */

@@ -296,6 +296,12 @@ static void run_cluster(int nit, int work, int smem, uint4* slots, unsigned* gen
   }
 }
 
+static double first_out(double* out) {
+  double h = 0.0;
+  CK(cudaMemcpy(&h, out, sizeof(double), cudaMemcpyDeviceToHost));
+  return h;
+}
+
 int main(int argc, char** argv) {
   const int nit = argc > 1 ? atoi(argv[1]) : 4000;
   const int work = 150;   // dependent fp64 FMAs per iteration (~600 cycles): stands for the SpMV + updates
@@ -322,12 +328,13 @@ int main(int argc, char** argv) {
   CK(cudaMemset(slots, 0, sizeof(uint4) * 2 * (HF_MAX_GRID + 1) * SLOT_U4));
   CK(cudaFuncSetAttribute(k_fx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(k_a2a, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  for (int G : {138, 148, 74, 37}) {
+  for (int G : {138, 37}) {
     for (int w : {work, 0}) {
       int nit_ = nit, w_ = w;
       void* a1[] = {&nit_, &w_, &acc, &acc_prev, &gen, &fail, &out};
       float ms = timed([&] { CK(cudaLaunchCooperativeKernel((const void*)k_fx, dim3(G), dim3(HF_PT), a1, smem, 0)); }, 3);
-      printf("fx     G=%3d work=%3d : %.3f us / iteration  (HF_NREP %d, poll delay %d)\n", G, w, ms * 1e3 / nit, HF_NREP, HF_POLL_DELAY);
+      printf("fx     G=%3d work=%3d : %.3f us / iteration  (HF_NREP %d, poll delay %d)  check %.15e\n", G, w, ms * 1e3 / nit, HF_NREP,
+             HF_POLL_DELAY, first_out(out));
       void* a2[] = {&nit_, &w_, &slots, &gen, &out};
       ms = timed([&] { CK(cudaLaunchCooperativeKernel((const void*)k_a2a, dim3(G), dim3(HF_PT), a2, smem, 0)); }, 3);
       printf("a2a    G=%3d work=%3d : %.3f us / iteration\n", G, w, ms * 1e3 / nit);
