@@ -112,6 +112,20 @@ def test_final_gather_gloo_world_size_2(tmp_path):
     assert ok.read_text() == "ok"
 
 
+def test_parameter_sweep_driver_gloo_world_size_2(tmp_path):
+    # the sweep driver under torchrun, 2 ranks, gloo: per-rank output writing, one final gather, a failing rank
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(HERE, "_gloo_psweep_worker.py"), str(tmp_path)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert (tmp_path / "ok.txt").read_text() == "ok"
+
+
 class _FakeSolver:
     """Stands in for HeatSolver in the host-side tests of the serial sweep engine (no GPU)."""
 
