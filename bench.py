@@ -15,7 +15,7 @@ histories and final field out) inside the timed region.
 
 Extra objects on the JSON line:
   roofline      dominant kernel of the timed region.  At the cfg's own size the mesh fits on chip and the whole
-                solve runs in ``k_pcg_patch``: bound by the latency of its grid reduction, so the object says
+                solve runs in ``k_pcg_pipe`` / ``k_pcg_patch``: bound by the latency of its grid reduction, so the object says
                 ``bound: "latency"`` and reports its real DRAM rate and the time per PCG iteration.
   roofline_1m   ``k_pcg_stream`` (persistent streaming kernel, one cooperative launch per solve) on the >= 1 M-dof
                 refinement of ``cfgs/konopkova.yaml`` (BASELINE config #4), timed inside real solves;
@@ -291,7 +291,8 @@ def large_mesh_run(case, device, rtol, warm, recycle):
     _, iters, _ = s.run(case.amps, case.ic, case.coeff, [0])
     ms = s.stats()["run_ms"]
     s.close()
-    path = {1: "streaming kernel (launch per iteration)", 2: "persistent streaming kernel", 3: "on-chip patch kernel"}[path_id]
+    path = {1: "streaming kernel (launch per iteration)", 2: "persistent streaming kernel", 3: "on-chip patch kernel",
+            4: "on-chip patch kernel (pipelined CG)"}[path_id]
     return {"workload": f"{case.name} refined, N={n} dofs, nnz={nnz}, {case.num_steps} steps, {path}, "
                         f"recycled initial guess {recycle} vectors", "value": n * case.num_steps / (ms * 1e-3),
             "unit": "DOF-timesteps/s", "ms_per_step": ms / case.num_steps, "pcg_iterations_total": int(iters.sum())}
@@ -405,7 +406,7 @@ def run_ours(args, rank, world, local_rank):
             s.set_state(u_w)
             s.run(amps_t, c.ic, c.coeff, watch)
     path = s.solver_path()
-    kernel = {1: "k_pcg_iter", 2: "k_pcg_stream", 3: "k_pcg_patch"}[path]
+    kernel = {1: "k_pcg_iter", 2: "k_pcg_stream", 3: "k_pcg_patch", 4: "k_pcg_pipe"}[path]
     retries = s.stats()["retries"]
 
     # ---- sweep leg (config #5) through run_parameter_sweep
@@ -447,7 +448,7 @@ def run_ours(args, rank, world, local_rank):
         pass
     share = solve_ms / prof_run_ms if prof_run_ms > 0 else None
     its_total = max(1, int(iters_p.sum()))
-    if path == 3:
+    if path >= 3:
         # On chip: operator and vectors live in registers / shared memory for the whole solve.  Not an HBM-bound kernel:
         # its limit is the latency of one grid-wide reduction per PCG iteration, so the line reports the DRAM rate it
         # really sustains and the time per PCG iteration; the HBM-bound kernel of the code base is in roofline_1m.
@@ -508,7 +509,8 @@ def run_ours(args, rank, world, local_rank):
                                                                      traffic=traffic.get("k_pcg_iter_1m"), mode=1)
         line["konopkova_1m"] = large_mesh_run(cl, local_rank, args.rtol, args.warm_start, min(args.recycle, 64))
         # DRAM-honest: 4.3 M dofs, 580 MB per PCG iteration - nothing survives in the 126 MB L2 between iterations
-        line["roofline_4m"] = streaming_roofline(build_case("konopkova", 0.18), local_rank, args.rtol, peak, peak_src, steps=2,
+        # (bandwidth measurement only: the fast 'rows' mesher - Delaunay of 4.3 M points would take minutes)
+        line["roofline_4m"] = streaming_roofline(build_case("konopkova", 0.18, method="rows"), local_rank, args.rtol, peak, peak_src, steps=2,
                                                  traffic=traffic.get("k_pcg_stream_4m"))
         # the size of the reference's own gmsh meshes (2.1e5 - 4.3e5 nodes): still on chip
         line["mid_mesh"] = large_mesh_run(build_case(WORKLOAD, 0.6), local_rank, args.rtol, args.warm_start, args.recycle)

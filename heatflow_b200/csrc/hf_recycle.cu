@@ -36,7 +36,7 @@
 // One CTA per segment; every lane keeps its RC_SEG / 32 values of v in registers (consecutive-pair
 // loads) and the warps share the basis vectors (warp w takes k = w, w + 8, ...), so each warp has
 // RC_SEG / 64 independent 512-byte loads in flight per basis vector and no barrier is needed.
-__global__ void __launch_bounds__(RC_WARPS * 32)
+__global__ void __launch_bounds__(RC_WARPS * 32, 2)
 k_rc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double* __restrict__ v,
           double* __restrict__ parts, int m_extra, const double* __restrict__ extra) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -45,19 +45,36 @@ k_rc_dots(int m, int nseg, size_t ld, const double* __restrict__ V, const double
   double2 vv[RC_NV];
 #pragma unroll
   for (int j = 0; j < RC_NV; ++j) vv[j] = *reinterpret_cast<const double2*>(v + base + 64 * j);
-  for (int k = warp; k < m; k += RC_WARPS) {
+  // two basis vectors per pass: 2 x RC_NV independent 16-byte loads per lane in flight (8 KB per warp) before the
+  // first use, and the two shuffle trees overlap - the one-vector loop left the SM at 12 % warps active / 2.0 TB/s
+  for (int k = warp; k < m; k += 2 * RC_WARPS) {
+    const int k2 = k + RC_WARPS;
+    const bool two = k2 < m;
     const double* p = ((k == m_extra) ? extra : V + (size_t)k * ld) + base;   // the pending raw correction is not in a slot yet
-    double2 a[RC_NV];
+    const double* p2 = ((k2 == m_extra || !two) ? (two ? extra : p) : V + (size_t)k2 * ld) + (two ? base : 0);
+    double2 a[RC_NV], b[RC_NV];
 #pragma unroll
     for (int j = 0; j < RC_NV; ++j) a[j] = __ldcs(reinterpret_cast<const double2*>(p + 64 * j));
-    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < RC_NV; ++j) b[j] = __ldcs(reinterpret_cast<const double2*>(p2 + 64 * j));
+    double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
 #pragma unroll
     for (int j = 0; j < RC_NV; ++j) {
       s0 = fma(a[j].x, vv[j].x, s0);
       s1 = fma(a[j].y, vv[j].y, s1);
+      t0 = fma(b[j].x, vv[j].x, t0);
+      t1 = fma(b[j].y, vv[j].y, t1);
     }
-    const double s = hf_warp_sum(s0 + s1);
-    if (lane == 0) parts[(size_t)k * nseg + seg] = s;
+    double s = s0 + s1, t = t0 + t1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    if (lane == 0) {
+      parts[(size_t)k * nseg + seg] = s;
+      if (two) parts[(size_t)k2 * nseg + seg] = t;
+    }
   }
 }
 
@@ -144,59 +161,75 @@ k_rc_apply(int m, int n, size_t ld, double* __restrict__ W, double* __restrict__
     for (int k = threadIdx.x; k < m; k += HF_BLOCK) s_h[k] = hn[k];
   __syncthreads();
   double local = 0.0;
-  for (int i = blockIdx.x * HF_BLOCK + threadIdx.x; i < n; i += gridDim.x * HF_BLOCK) {
-    double ca0 = 0.0, ca1 = 0.0, cb0 = 0.0, cb1 = 0.0, ga0 = 0.0, ga1 = 0.0, gb0 = 0.0, gb1 = 0.0;
+  // two rows per thread (16-byte loads; n and ld are even), four basis vectors per pass: 8 + 8 independent loads in
+  // flight per thread.  Per row the sums run over k in the same order as a one-row loop would.
+  for (int i = 2 * (blockIdx.x * HF_BLOCK + threadIdx.x); i < n; i += 2 * gridDim.x * HF_BLOCK) {
+    double2 ca0 = {0.0, 0.0}, ca1 = {0.0, 0.0}, cb0 = {0.0, 0.0}, cb1 = {0.0, 0.0};
+    double2 ga0 = {0.0, 0.0}, ga1 = {0.0, 0.0}, gb0 = {0.0, 0.0}, gb1 = {0.0, 0.0};
     const double* w = W + i;
     const double* aw = AW + i;
+    auto ld2 = [](const double* q) {
+      double2 v;
+      asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(q));
+      return v;
+    };
+    auto acc = [](double c, const double2& v, double2& s) {
+      s.x = fma(c, v.x, s.x);
+      s.y = fma(c, v.y, s.y);
+    };
     int k = 0;
     for (; k + 4 <= m; k += 4) {
-      const double w0 = hf_ld_stream(w + (size_t)k * ld), w1 = hf_ld_stream(w + (size_t)(k + 1) * ld),
-                   w2 = hf_ld_stream(w + (size_t)(k + 2) * ld), w3 = hf_ld_stream(w + (size_t)(k + 3) * ld);
-      const double z0 = hf_ld_stream(aw + (size_t)k * ld), z1 = hf_ld_stream(aw + (size_t)(k + 1) * ld),
-                   z2 = hf_ld_stream(aw + (size_t)(k + 2) * ld), z3 = hf_ld_stream(aw + (size_t)(k + 3) * ld);
+      const double2 w0 = ld2(w + (size_t)k * ld), w1 = ld2(w + (size_t)(k + 1) * ld), w2 = ld2(w + (size_t)(k + 2) * ld),
+                    w3 = ld2(w + (size_t)(k + 3) * ld);
+      const double2 z0 = ld2(aw + (size_t)k * ld), z1 = ld2(aw + (size_t)(k + 1) * ld), z2 = ld2(aw + (size_t)(k + 2) * ld),
+                    z3 = ld2(aw + (size_t)(k + 3) * ld);
       const double c0 = s_c[k], c1 = s_c[k + 1], c2 = s_c[k + 2], c3 = s_c[k + 3];
-      ca0 = fma(c0, w0, ca0);
-      ca1 = fma(c1, w1, ca1);
-      ca0 = fma(c2, w2, ca0);
-      ca1 = fma(c3, w3, ca1);
-      cb0 = fma(c0, z0, cb0);
-      cb1 = fma(c1, z1, cb1);
-      cb0 = fma(c2, z2, cb0);
-      cb1 = fma(c3, z3, cb1);
+      acc(c0, w0, ca0);
+      acc(c1, w1, ca1);
+      acc(c2, w2, ca0);
+      acc(c3, w3, ca1);
+      acc(c0, z0, cb0);
+      acc(c1, z1, cb1);
+      acc(c2, z2, cb0);
+      acc(c3, z3, cb1);
       if (PENDING) {
         const double h0 = s_h[k], h1 = s_h[k + 1], h2 = s_h[k + 2], h3 = s_h[k + 3];
-        ga0 = fma(h0, w0, ga0);
-        ga1 = fma(h1, w1, ga1);
-        ga0 = fma(h2, w2, ga0);
-        ga1 = fma(h3, w3, ga1);
-        gb0 = fma(h0, z0, gb0);
-        gb1 = fma(h1, z1, gb1);
-        gb0 = fma(h2, z2, gb0);
-        gb1 = fma(h3, z3, gb1);
+        acc(h0, w0, ga0);
+        acc(h1, w1, ga1);
+        acc(h2, w2, ga0);
+        acc(h3, w3, ga1);
+        acc(h0, z0, gb0);
+        acc(h1, z1, gb1);
+        acc(h2, z2, gb0);
+        acc(h3, z3, gb1);
       }
     }
     for (; k < m; ++k) {
-      const double wk = hf_ld_stream(w + (size_t)k * ld), zk = hf_ld_stream(aw + (size_t)k * ld);
-      ca0 = fma(s_c[k], wk, ca0);
-      cb0 = fma(s_c[k], zk, cb0);
+      const double2 wk = ld2(w + (size_t)k * ld), zk = ld2(aw + (size_t)k * ld);
+      acc(s_c[k], wk, ca0);
+      acc(s_c[k], zk, cb0);
       if (PENDING) {
-        ga0 = fma(s_h[k], wk, ga0);
-        gb0 = fma(s_h[k], zk, gb0);
+        acc(s_h[k], wk, ga0);
+        acc(s_h[k], zk, gb0);
       }
     }
-    double ca = ca0 + ca1, cb = cb0 + cb1;
+    double2 ca = {ca0.x + ca1.x, ca0.y + ca1.y}, cb = {cb0.x + cb1.x, cb0.y + cb1.y};
     if (PENDING) {
-      const double wm = d[i] + (ga0 + ga1), awm = ad[i] + (gb0 + gb1);
-      W[(size_t)m * ld + i] = wm;
-      AW[(size_t)m * ld + i] = awm;
-      ca = fma(s_c[m], wm, ca);
-      cb = fma(s_c[m], awm, cb);
+      const double2 dv = *reinterpret_cast<const double2*>(d + i), adv = *reinterpret_cast<const double2*>(ad + i);
+      const double2 wm = {dv.x + (ga0.x + ga1.x), dv.y + (ga0.y + ga1.y)};
+      const double2 awm = {adv.x + (gb0.x + gb1.x), adv.y + (gb0.y + gb1.y)};
+      *reinterpret_cast<double2*>(W + (size_t)m * ld + i) = wm;
+      *reinterpret_cast<double2*>(AW + (size_t)m * ld + i) = awm;
+      acc(s_c[m], wm, ca);
+      acc(s_c[m], awm, cb);
     }
-    const double x = a[i] + ca, r = b[i] - cb;
-    a[i] = x;
-    b[i] = r;
-    if (x0save) x0save[i] = x;
-    local = fma(r, r, local);
+    const double2 av = *reinterpret_cast<const double2*>(a + i), bv = *reinterpret_cast<const double2*>(b + i);
+    const double2 x = {av.x + ca.x, av.y + ca.y}, r = {bv.x - cb.x, bv.y - cb.y};
+    *reinterpret_cast<double2*>(a + i) = x;
+    *reinterpret_cast<double2*>(b + i) = r;
+    if (x0save) *reinterpret_cast<double2*>(x0save + i) = x;
+    local = fma(r.x, r.x, local);
+    local = fma(r.y, r.y, local);
   }
   const double tot = hf_block_sum(local, sh);
   if (threadIdx.x == 0) part[blockIdx.x] = tot;

@@ -62,6 +62,7 @@ class Mesh:
     # extra knobs of the in-repo mesher (not in the reference); defaults reproduce cfg sizes
     growth = 1.3
     size_scale = 1.0
+    method = "quadtree"       # 'quadtree' (graded points + Delaunay, quality bound) or 'rows' (round-1 row zipper)
 
     def __init__(self, name, boundaries, materials):
         if not isinstance(name, str):
@@ -98,7 +99,7 @@ class Mesh:
             self.material_tags[mat.name] = i + 1
         self.mesh = triangulate_rectangles(
             [m.boundaries for m in self.materials], [m.mesh_size for m in self.materials],
-            bounds=self.boundaries, growth=self.growth, size_scale=self.size_scale)
+            bounds=self.boundaries, growth=self.growth, size_scale=self.size_scale, method=self.method)
         return self.mesh
 
     def to_dolfinx(self, *, comm=COMM, gdim: int = 2, rank: int = 0):

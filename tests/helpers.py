@@ -28,7 +28,7 @@ class Case:
     pass
 
 
-def build_case(cfg_name="geballe_no_diamond", size_scale=8.0, growth=1.3):
+def build_case(cfg_name="geballe_no_diamond", size_scale=8.0, growth=1.3, method=None):
     """Mesh + problem data for a cfg at a coarsened mesh size (size_scale > 1 = coarser)."""
     cfg = load_cfg(cfg_name)
     with_diamond = "p_diam" in cfg["mats"]
@@ -36,6 +36,8 @@ def build_case(cfg_name="geballe_no_diamond", size_scale=8.0, growth=1.3):
     mesh = Mesh("mesh.msh", bounds, mats)
     mesh.size_scale = size_scale
     mesh.growth = growth
+    if method is not None:
+        mesh.method = method
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         arrays = mesh.build_mesh()

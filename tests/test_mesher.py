@@ -20,14 +20,51 @@ def _signed_area(nodes, tris):
     return 0.5 * ((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]))
 
 
-@pytest.fixture(scope="module", params=[("geballe_with_diamond", 4.0), ("geballe_no_diamond", 4.0)])
+@pytest.fixture(scope="module", params=[("geballe_with_diamond", 4.0, "quadtree"), ("geballe_no_diamond", 4.0, "quadtree"),
+                                        ("geballe_with_diamond", 4.0, "rows"), ("geballe_no_diamond", 4.0, "rows")],
+                ids=lambda p: f"{p[0]}-{p[2]}")
 def meshed(request):
-    name, scale = request.param
+    name, scale, method = request.param
     cfg = load_cfg(name)
     stack = problem.stack_with_diamond if "p_diam" in cfg["mats"] else problem.stack_no_diamond
     mats, bounds, _ = stack(cfg)
-    m = triangulate_rectangles([x.boundaries for x in mats], [x.mesh_size for x in mats], size_scale=scale)
+    m = triangulate_rectangles([x.boundaries for x in mats], [x.mesh_size for x in mats], size_scale=scale, method=method)
+    m.method = method
     return mats, m, scale
+
+
+def _angles_and_aspect(nodes, tris):
+    """(smallest angle, largest angle) in degrees and longest edge / height on it, per triangle."""
+    p = nodes[tris]
+    a = np.linalg.norm(p[:, 1] - p[:, 2], axis=1)
+    b = np.linalg.norm(p[:, 0] - p[:, 2], axis=1)
+    c = np.linalg.norm(p[:, 0] - p[:, 1], axis=1)
+    A = np.arccos(np.clip((b * b + c * c - a * a) / (2 * b * c), -1, 1))
+    B = np.arccos(np.clip((a * a + c * c - b * b) / (2 * a * c), -1, 1))
+    ang = np.degrees(np.stack([A, B, np.pi - A - B], axis=1))
+    longest = np.maximum.reduce([a, b, c])
+    return ang.min(axis=1), ang.max(axis=1), longest / (2.0 * np.abs(_signed_area(nodes, tris)) / longest)
+
+
+@pytest.mark.parametrize("name", ["geballe_no_diamond", "geballe_with_diamond", "konopkova"])
+def test_mesh_quality_bound_at_cfg_sizes(name):
+    # SURVEY section 8 f3: the graded transition from 0.02 um (coupler) to 10 um (diamond, gasket) cells at the cfgs' own
+    # sizes keeps every triangle well shaped - the reference gets this from gmsh's Delaunay / frontal mesher
+    # (mesh_and_materials/mesh.py:129-147)
+    cfg = load_cfg(name)
+    stack = problem.stack_with_diamond if "p_diam" in cfg["mats"] else problem.stack_no_diamond
+    mats, _, _ = stack(cfg)
+    m = triangulate_rectangles([x.boundaries for x in mats], [x.mesh_size for x in mats])
+    amin, amax, aspect = _angles_and_aspect(m.nodes, m.tris)
+    assert amin.min() >= 12.0, amin.min()
+    assert amax.max() <= 135.0, amax.max()
+    assert aspect.max() <= 6.0, aspect.max()
+    assert np.mean(amin >= 30.0) >= 0.97                     # the bulk is (near) right isosceles
+    assert 1.0e5 < m.num_nodes < 1.6e5
+    # round-1 row mesher on the same input, for the record: slivers wherever fine rows run out to coarse radii
+    if name != "geballe_no_diamond":
+        rows = triangulate_rectangles([x.boundaries for x in mats], [x.mesh_size for x in mats], method="rows")
+        assert _angles_and_aspect(rows.nodes, rows.tris)[0].min() < 1.0
 
 
 def test_conforming_positive_and_covering(meshed):
@@ -59,15 +96,17 @@ def test_tags_and_sizes_follow_materials(meshed):
     p_ins = mats[[x.name for x in mats].index("p_ins")]
     zi = p_ins.boundaries[1]
     tz = m.nodes[m.tris][:, :, 0]
-    assert not np.any((tz.min(axis=1) < zi - 1e-15) & (tz.max(axis=1) > zi + 1e-15))
+    over = cent[:, 1] < p_ins.boundaries[3]                            # the radii over which that interface exists
+    assert not np.any(over & (tz.min(axis=1) < zi - 1e-15) & (tz.max(axis=1) > zi + 1e-15))
 
 
 def test_deterministic_and_row_major_band(meshed):
     mats, m, scale = meshed
-    m2 = triangulate_rectangles([x.boundaries for x in mats], [x.mesh_size for x in mats], size_scale=scale)
+    m2 = triangulate_rectangles([x.boundaries for x in mats], [x.mesh_size for x in mats], size_scale=scale, method=m.method)
     assert np.array_equal(m.nodes, m2.nodes) and np.array_equal(m.tris, m2.tris)
-    band = np.abs(m.tris[:, [0, 1, 2]] - m.tris[:, [1, 2, 0]]).max()
-    assert band <= 2 * np.diff(m.row_ptr).max() + 2                   # neighbours live in adjacent z-rows
+    if m.method == "rows":
+        band = np.abs(m.tris[:, [0, 1, 2]] - m.tris[:, [1, 2, 0]]).max()
+        assert band <= 2 * np.diff(m.row_ptr).max() + 2               # neighbours live in adjacent z-rows
     assert np.all(np.diff(m.nodes[:, 0]) >= 0)                        # z-major node order
 
 
@@ -81,9 +120,13 @@ def test_refinement_knob_scales_dof_count():
 
 def test_layout_with_hole_and_invalid_input():
     rects = [[0, 1, 0, 1], [1, 2, 0, 1], [0, 1, 1, 2]]                # L-shape: box [1,2]x[1,2] is empty
-    m = triangulate_rectangles(rects, [0.25, 0.25, 0.5])
-    assert abs(_signed_area(m.nodes, m.tris).sum() - 3.0) < 1e-12
-    assert not np.any((m.nodes[:, 0] > 1 + 1e-12) & (m.nodes[:, 1] > 1 + 1e-12))
+    for method in ("quadtree", "rows"):
+        m = triangulate_rectangles(rects, [0.25, 0.25, 0.5], method=method)
+        assert abs(_signed_area(m.nodes, m.tris).sum() - 3.0) < 1e-12
+        assert not np.any((m.nodes[:, 0] > 1 + 1e-12) & (m.nodes[:, 1] > 1 + 1e-12))
+        assert np.unique(m.tris).size == m.num_nodes
+    with pytest.raises(ValueError):
+        triangulate_rectangles(rects, [0.25, 0.25, 0.5], method="gmsh")
     with pytest.raises(ValueError):
         triangulate_rectangles([], [])
     with pytest.raises(ValueError):
