@@ -28,8 +28,9 @@ class Case:
     pass
 
 
-def build_case(cfg_name="geballe_no_diamond", size_scale=8.0, growth=1.3, method=None):
-    """Mesh + problem data for a cfg at a coarsened mesh size (size_scale > 1 = coarser)."""
+def build_case(cfg_name="geballe_no_diamond", size_scale=8.0, growth=1.3, method=None, arrays=None):
+    """Mesh + problem data for a cfg at a coarsened mesh size (size_scale > 1 = coarser).  `arrays`
+    (nodes, tris, cell_tag): use this mesh instead of running the mesher (reference golden files)."""
     cfg = load_cfg(cfg_name)
     with_diamond = "p_diam" in cfg["mats"]
     mats, bounds, info = (problem.stack_with_diamond if with_diamond else problem.stack_no_diamond)(cfg)
@@ -39,8 +40,14 @@ def build_case(cfg_name="geballe_no_diamond", size_scale=8.0, growth=1.3, method
     if method is not None:
         mesh.method = method
     import contextlib, io
-    with contextlib.redirect_stdout(io.StringIO()):
-        arrays = mesh.build_mesh()
+    if arrays is not None:
+        from heatflow_b200.mesh_and_materials.mesher import MeshArrays
+        for tag, m in enumerate(mats, start=1):                # tag = material list index + 1 (mesh.py:113-126)
+            m._tag = m.tag = tag
+        arrays = MeshArrays(*arrays)
+    else:
+        with contextlib.redirect_stdout(io.StringIO()):
+            arrays = mesh.build_mesh()
     c = Case()
     c.name = cfg_name
     c.cfg, c.mats, c.bounds, c.arrays = cfg, mats, bounds, arrays
