@@ -55,6 +55,7 @@ SIGNATURES = {
     "hf_ens_create": (C.c_int, [_vp, _i32, _vp, _vp, _i32]),
     "hf_ens_run": (C.c_int, [_vp, _i32, _vp, _f64, _i32, _vp, _vp, _vp]),
     "hf_ens_get_state": (C.c_int, [_vp, _vp]),
+    "hf_ens_get_path": (C.c_int, [_vp]),
     "hf_ens_destroy": (C.c_int, [_vp]),
 }
 

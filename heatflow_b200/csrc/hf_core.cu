@@ -634,6 +634,11 @@ extern "C" int hf_build_operator(hf_ctx* c, double dt, int32_t axisymmetric) {
     HF_TRY(hf_patch_plan(c, c->opA));
   }
   c->valM1.release();
+  // the pipelined on-chip kernel (k_pcg_pipe) trades one reduction trip for a longer recurrence chain: fine for the
+  // mass-dominated transient operator (measured 1e-12 .. 1.5e-11 against the LU oracle), not for a pure stiffness
+  // operator (steady state, cond ~ 1e8: its recurrence residual drifts to ~1e-5 of the true one) - those keep classic CG
+  c->op_transient = !c->mat_rhoc.empty();
+  for (double rc : c->mat_rhoc) c->op_transient = c->op_transient && rc > 0.0;
   c->op_built = true;
   c->proj_built = false;
   c->last_iters = 0;

@@ -206,6 +206,7 @@ struct hf_ctx {
   DevBuf<double> gfull;                // g on Dirichlet dofs, 0 elsewhere
   // operator
   bool op_built = false;
+  bool op_transient = true;            // every material has rho c > 0 (mass term present): the pipelined CG kernel may be used
   double dt = 0.0;
   int axisym = 1;
   DevBuf<double> valM, valA0, valA, valM1;

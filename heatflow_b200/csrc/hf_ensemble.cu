@@ -28,55 +28,7 @@
 #include <algorithm>
 #include <cmath>
 
-#include "hf_ctx.cuh"
-
-#define HF_EB 32            // max variants per tile
-#define HF_ET 256           // threads per CTA of the set-up kernels
-#define HF_ENT 512          // threads per CTA of the iteration kernel
-#define HF_EPAIRS 1024      // (row, variant) pairs per chunk: R = HF_EPAIRS / B rows
-#define HF_ERPT (HF_EPAIRS / HF_ENT)
-#define HF_EHPT 4           // halo pairs per thread carried in registers
-
-struct EnsCtrl {
-  int done, it, n_active, pad;
-  unsigned counter[4];
-  int active[HF_EB];
-  double thr[HF_EB], rz[HF_EB], alpha[HF_EB], beta[HF_EB], bn[HF_EB];
-};
-
-struct EnsState {
-  int B = 0, LB = 0;        // tile width (power of two) and its log2
-  int nb = 0;               // real variants in the tile (<= B)
-  int grid = 0;             // CTAs of the set-up kernels
-  int last_iters = 0;
-  DevBuf<double> base0, s0;           // [nnz]
-  DevBuf<double> ks, coeff;           // [B]
-  DevBuf<double> dg, g, u, uprev, x, z, z1, p0, p1, w, w1;   // [Nalloc*B]; dg = diagonal of A_b (0 on Dirichlet rows)
-  bool have_prev = false;
-  DevBuf<double> part;                // [4][CTAs][B]
-  // patch decomposition for the iteration kernel
-  int R = 0, nchunks = 0, halo_max = 0, halo_cap = 0, mcap = 0, nstages = 0, igrid = 0;
-  size_t stage_bytes = 0, iter_smem = 0;
-  DevBuf<int> halo_ptr, halo_idx;
-  DevBuf<int> rowptr_pad;             // CSR row pointers padded to whole chunks + 4
-  DevBuf<int> lc_off;                 // [nchunks+1] offsets of the chunks' column blocks (multiples of 8)
-  DevBuf<unsigned short> lcol;        // local columns, chunk blocks padded to 16 bytes
-  DevBuf<double2> bs;                 // {base0, S0} per CSR slot (16 bytes: any row range is TMA-aligned)
-  // recycled initial guess, one basis per variant (same scheme as hf_recycle.cu): slots of [nb] doubles in the
-  // [row, variant] layout; W = corrections, AW = D^-1 A_b W, inv[slot, b] = 1 / (w . A_b w)
-  int rc_cap = 0, rc_count = 0, rc_nseg = 0;
-  DevBuf<double> rc_W, rc_AW, rc_inv, rc_coef, rc_parts, rc_part_nn, rc_d, rc_ad;
-  DevBuf<EnsCtrl> ctrl;
-  EnsCtrl* h_ctrl = nullptr;          // pinned mirror
-  DevBuf<double> hist, stage;
-  DevBuf<int> watch;
-  cudaGraphExec_t chunk_exec[3] = {nullptr, nullptr, nullptr};
-  ~EnsState() {
-    for (auto& g : chunk_exec)
-      if (g) cudaGraphExecDestroy(g);
-    if (h_ctrl) cudaFreeHost(h_ctrl);
-  }
-};
+#include "hf_ens.cuh"
 
 void hf_ens_free(hf_ctx* c) {
   delete c->ens;
@@ -869,6 +821,9 @@ extern "C" int hf_ens_create(hf_ctx* c, int32_t batch, const double* k_sample, c
   int hbad = 0;
   HF_TRY(bad.download(&hbad, 1, c->stream));
   if (hbad) return hf_fail(HF_ERR_STATE, "ensemble operator has a non-positive diagonal at row " + std::to_string(hbad - 1));
+  // meshes that fit on chip: one cooperative launch per solve for the whole tile (hf_enspatch.cu)
+  const int mode = c->force_mode >= 0 ? c->force_mode : c->mode;
+  if (mode == 0 || mode >= 3) HF_TRY(hf_ens_oc_plan(c, e));
   return HF_OK;
 }
 
@@ -1022,7 +977,19 @@ extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double 
       e->rc_count = 0;
     }
   }
+  bool on_chip = e->oc_ok;
+  if (on_chip) {
+    // asynchronous solves: iteration counts and failures are read once at the end; the state at the start of the
+    // run is kept so that a failed run can be repeated with the host-polled streaming kernels (as hf_run does)
+    if (e->oc_iters.n < (size_t)std::max(1, n_steps)) HF_TRY(e->oc_iters.alloc(std::max(1, n_steps), c->stream));
+    HF_CUDA(cudaMemsetAsync(e->oc_fail.p, 0, sizeof(int), c->stream));
+    if (e->oc_u0.n != 2 * nbp) HF_TRY(e->oc_u0.alloc(2 * nbp, c->stream));
+    HF_CUDA(cudaMemcpyAsync(e->oc_u0.p, e->u.p, sizeof(double) * nbp, cudaMemcpyDeviceToDevice, c->stream));
+    HF_CUDA(cudaMemcpyAsync(e->oc_u0.p + nbp, e->uprev.p, sizeof(double) * nbp, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  const bool had_prev = e->have_prev;
   HF_CUDA(cudaEventRecord(c->ev0, c->stream));
+run_again:
   for (int s = 0; s < n_steps; ++s) {
     if (c->n_gauss) {
       const int n = c->n_gauss * B;
@@ -1038,9 +1005,10 @@ extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double 
     HF_CUDA(cudaGetLastError());
     HF_TRY(ens_rc_project(c, e, nbp));
     int it = 0;
-    HF_TRY(ens_solve(c, e, &it));
+    if (on_chip) HF_TRY(hf_ens_oc_solve_async(c, e, s));
+    else HF_TRY(ens_solve(c, e, &it));
     HF_TRY(ens_rc_store(c, e, nbp));
-    if (iters) iters[s] = it;
+    if (iters && !on_chip) iters[s] = it;
     if (n_watch) {
       const int n = n_watch * B;
       ENS_DISPATCH(e->LB, k_ens_sample<LB><<<(n + 255) / 256, 256, 0, c->stream>>>(n_watch, n_steps, s, e->watch.p, e->x.p, e->hist.p));
@@ -1049,6 +1017,28 @@ extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double 
     std::swap(e->u.p, e->uprev.p);      // u_{n-1} <- u_n (neither array is an argument of the captured graphs)
     HF_CUDA(cudaMemcpyAsync(e->u.p, e->x.p, sizeof(double) * nb, cudaMemcpyDeviceToDevice, c->stream));
     e->have_prev = true;
+  }
+  if (on_chip && n_steps) {
+    int nfail = 0;
+    HF_TRY(e->oc_fail.download(&nfail, 1, c->stream));
+    if (nfail) {
+      // an on-chip solve hit the iteration cap or left the fixed-point range of its reduction: the state it left is
+      // not trustworthy, the whole run is repeated from its initial state with the streaming kernels (still the GPU)
+      c->stat_retries += 1;
+      HF_CUDA(cudaMemcpyAsync(e->u.p, e->oc_u0.p, sizeof(double) * nbp, cudaMemcpyDeviceToDevice, c->stream));
+      HF_CUDA(cudaMemcpyAsync(e->uprev.p, e->oc_u0.p + nbp, sizeof(double) * nbp, cudaMemcpyDeviceToDevice, c->stream));
+      e->have_prev = had_prev;
+      e->rc_count = 0;                                       // the recycled basis of the failed run is dropped as well
+      on_chip = false;
+      goto run_again;
+    }
+    std::vector<int> hit(n_steps);
+    HF_TRY(e->oc_iters.download(hit.data(), n_steps, c->stream));
+    for (int s = 0; s < n_steps; ++s) {
+      if (iters) iters[s] = hit[s];
+      c->stat_iters += (unsigned long long)hit[s];
+    }
+    e->last_iters = hit[n_steps - 1];
   }
   HF_CUDA(cudaEventRecord(c->ev1, c->stream));
   if (n_watch && n_steps)   // device layout [B, S, W]; only the first nb variants are real
@@ -1070,6 +1060,11 @@ extern "C" int hf_ens_get_state(hf_ctx* c, double* u) {
                                                                                             e->u.p, e->stage.p));
   HF_CUDA(cudaGetLastError());
   return e->stage.download(u, (size_t)c->N * e->nb, c->stream);
+}
+
+extern "C" int hf_ens_get_path(hf_ctx* c) {
+  if (!c || !c->ens) return hf_fail(HF_ERR_STATE, "hf_ens_get_path: no ensemble");
+  return c->ens->oc_ok ? 5 : 1;
 }
 
 extern "C" int hf_ens_destroy(hf_ctx* c) {

@@ -662,7 +662,7 @@ static const void* pipe_kernel(int rpt, int share) {
 bool hf_patch_pipelined(const hf_ctx* c, const SellOp& vals) {
   const SellOp& op = vals.plan_from ? *vals.plan_from : vals;
   const int mode = c->force_mode >= 0 ? c->force_mode : c->mode;
-  return op.pp_rpt != 0 && mode != 4 && pipe_kernel(op.pp_rpt, op.pp_share) != nullptr;
+  return op.pp_rpt != 0 && mode != 4 && c->op_transient && pipe_kernel(op.pp_rpt, op.pp_share) != nullptr;
 }
 static int patch_set_smem_rpt(int rpt, int share, size_t bytes) {
   HF_CUDA(cudaFuncSetAttribute(patch_kernel(rpt, share), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

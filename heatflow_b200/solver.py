@@ -245,6 +245,13 @@ class HeatSolver:
         _lib.check(self._L.hf_ens_get_state(self._h, _lib.ptr(u)))
         return u
 
+    def ens_path(self):
+        """1: streaming ensemble kernels, 5: batched on-chip kernel (one launch per time step)."""
+        p = self._L.hf_ens_get_path(self._h)
+        if p < 0:
+            _lib.check(p)
+        return p
+
     def ens_destroy(self):
         _lib.check(self._L.hf_ens_destroy(self._h))
         self.ens_batch = 0

@@ -183,6 +183,10 @@ int hf_ens_run(hf_ctx* ctx, int32_t n_steps, const double* amp, double t_ic,
                int32_t n_watch, const int32_t* watch_nodes, double* hist /*[B,n_steps,n_watch]*/,
                int32_t* iters /*[n_steps]*/);
 int hf_ens_get_state(hf_ctx* ctx, double* u /*[B,N]*/);
+/* Which kernels advance the current tile: 1 = streaming ensemble kernels (one launch per PCG iteration, operator read
+ * from HBM once per tile and iteration), 5 = batched on-chip kernel (one cooperative launch per time step; tiles of
+ * up to 4 variants on meshes whose 1024-row patches fit the SMs).  No reference counterpart (diagnostics). */
+int hf_ens_get_path(hf_ctx* ctx);
 int hf_ens_destroy(hf_ctx* ctx);
 
 #ifdef __cplusplus
