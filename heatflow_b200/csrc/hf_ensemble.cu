@@ -988,6 +988,14 @@ extern "C" int hf_ens_run(hf_ctx* c, int32_t n_steps, const double* amp, double 
     HF_CUDA(cudaMemcpyAsync(e->oc_u0.p + nbp, e->uprev.p, sizeof(double) * nbp, cudaMemcpyDeviceToDevice, c->stream));
   }
   const bool had_prev = e->have_prev;
+  c->stat_solve_ms = 0.0;
+  c->stat_solve_launches = 0;
+  if (c->profile)                                           // hf_set_profile: CUDA events around every solve
+    while (c->prof_ev.size() < (size_t)2 * n_steps) {
+      cudaEvent_t ev;
+      HF_CUDA(cudaEventCreate(&ev));
+      c->prof_ev.push_back(ev);
+    }
   HF_CUDA(cudaEventRecord(c->ev0, c->stream));
 run_again:
   for (int s = 0; s < n_steps; ++s) {
@@ -1005,8 +1013,11 @@ run_again:
     HF_CUDA(cudaGetLastError());
     HF_TRY(ens_rc_project(c, e, nbp));
     int it = 0;
+    const bool prof = c->profile && (size_t)(2 * s + 1) < c->prof_ev.size();
+    if (prof) HF_CUDA(cudaEventRecord(c->prof_ev[2 * s], c->stream));
     if (on_chip) HF_TRY(hf_ens_oc_solve_async(c, e, s));
     else HF_TRY(ens_solve(c, e, &it));
+    if (prof) HF_CUDA(cudaEventRecord(c->prof_ev[2 * s + 1], c->stream));
     HF_TRY(ens_rc_store(c, e, nbp));
     if (iters && !on_chip) iters[s] = it;
     if (n_watch) {
@@ -1047,6 +1058,12 @@ run_again:
   float ms = 0.f;
   HF_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->stat_run_ms = ms;
+  if (c->profile)
+    for (int s = 0; s < n_steps; ++s) {
+      float t = 0.f;
+      HF_CUDA(cudaEventElapsedTime(&t, c->prof_ev[2 * s], c->prof_ev[2 * s + 1]));
+      c->stat_solve_ms += t;
+    }
   return HF_OK;
 }
 

@@ -53,6 +53,7 @@ struct EnsOcArgs {
   unsigned long long* acc;
   int* iters_out;
   int* fail;
+  long long* phase;              // diagnostics (-DHF_PHASE_TIMING): [G][2][8] clock64 cycles per phase, warps 0 and 1
 };
 
 // ---- exact one-trip grid reduction (see hf_persist.cuh) for NV values per variant of one half-tile -------------
@@ -164,41 +165,50 @@ __device__ __forceinline__ void ep_wait(double (&out)[NV], EbFn eb_of, unsigned 
   }
 }
 
-// BG consecutive doubles of one row (16-byte aligned when BG is even)
-template <int BG>
-__device__ __forceinline__ void ep_gather(const double* p, double (&v)[BG]) {
-  if constexpr (BG % 2 == 0) {
-#pragma unroll
-    for (int j = 0; j < BG / 2; ++j) {
-      const double2 t = reinterpret_cast<const double2*>(p)[j];
-      v[2 * j] = t.x;
-      v[2 * j + 1] = t.y;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < BG; ++j) v[j] = p[j];
-  }
-}
+// ---------------------------------------------------------------------------------------
+// The kernel: a tile of 4 variants in NH half-tiles of BG = 4 / NH variants.
+// Shared-memory vectors are stored pair-major: element (row, b) of an array with `rows` rows sits at
+// ((b >> 1) * rows + row) * 2 + (b & 1), i.e. one double2 per (variant pair, row).  A gather of column c for a pair is
+// one 16-byte load whose bank group is c mod 8 - consecutive columns never collide, whereas the [row][4] layout
+// (32-byte stride) leaves half of the banks idle and serialises neighbouring columns two by two.
+// ---------------------------------------------------------------------------------------
+#ifdef HF_PHASE_TIMING
+#define EP_PT_DECL long long pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_t0 = clock64();
+#define EP_PT_MARK(i)                 \
+  do {                                \
+    const long long t1__ = clock64(); \
+    pt_acc[i] += t1__ - pt_t0;        \
+    pt_t0 = t1__;                     \
+  } while (0)
+#define EP_PT_STORE                                                                         \
+  if (P.phase && lane == 0 && warp < 2)                                                     \
+    for (int i__ = 0; i__ < 8; ++i__) P.phase[((size_t)blockIdx.x * 2 + warp) * 8 + i__] = pt_acc[i__];
+#else
+#define EP_PT_DECL
+#define EP_PT_MARK(i)
+#define EP_PT_STORE
+#endif
 
-// ---------------------------------------------------------------------------------------
-// The kernel.  B variants in NH half-tiles of BG = B / NH variants.
-// ---------------------------------------------------------------------------------------
-template <int LB, int NH>
+template <int NH>
 __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
-  constexpr int B = 1 << LB;
-  constexpr int BG = B / NH;
+  constexpr int B = 4;
+  constexpr int BG = B / NH;          // variants per half-tile
+  constexpr int NPG = BG / 2;         // variant pairs per half-tile
   constexpr int R = EP_R;
   constexpr int NSL = R / 32;
   constexpr int NVM = 3;
   static_assert(NSL == 32, "one slice per lane in the offset scan");
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int RH = R + P.halo_cap, HC = P.halo_cap;
   double* sval = reinterpret_cast<double*>(smem_raw);            // operator entries beyond the register cache
   double* ss0 = sval + P.mat_cap;                                // S0 entries of the flagged slices
-  double* sp = ss0 + P.s0_cap;                                   // p: [(R + halo) , B]
-  double* szh = sp + (size_t)(R + P.halo_cap) * B;               // z on the halo rows
-  double* swh = szh + (size_t)P.halo_cap * B;                    // w on the halo rows (validated packets)
-  double* sdinv = swh + (size_t)P.halo_cap * B;                  // 1 / d on the own rows (0 on Dirichlet rows)
-  double* sred = sdinv + (size_t)R * B;                          // [NH][2][EP_W][BG * 3]
+  double2* sp = reinterpret_cast<double2*>(ss0 + P.s0_cap);      // p: [2 pairs][R + halo]
+  double2* szh = sp + 2 * (size_t)RH;                            // z on the halo rows: [2 pairs][halo]
+  double2* swh = szh + 2 * (size_t)HC;                           // w on the halo rows (validated packets)
+  double2* sdinv = swh + 2 * (size_t)HC;                         // 1 / d on the own rows (0 on Dirichlet rows): [2][R]
+  double2* swo = sdinv + 2 * (size_t)R;                          // w on the own rows (phase 1 -> phase 2): [2][R]
+  double2* szo = swo + 2 * (size_t)R;                            // z on the own rows: [2][R]
+  double* sred = reinterpret_cast<double*>(szo + 2 * (size_t)R);     // [NH][2][EP_W][BG * 3]
   double* s_alpha = sred + NH * 2 * EP_W * BG * NVM;             // per variant: alpha, beta, rz, rz_ref, pp, thr, ks
   double* s_beta = s_alpha + B;
   double* s_rz = s_beta + B;
@@ -208,9 +218,9 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
   double* s_ks = s_thr + B;
   unsigned long long* s_prev = reinterpret_cast<unsigned long long*>(s_ks + B);   // [NH][2][32][2 * 3]
   int* s_act = reinterpret_cast<int*>(s_prev + NH * 2 * 32 * 2 * NVM);           // [B]
-  int* s_ctl = s_act + B;                                        // [NH][4]: check, done, since, it
+  int* s_ctl = s_act + B;                                        // [NH][4]: check, done, since, -
   int* shal = s_ctl + NH * 4;
-  int* sbase = shal + P.halo_cap;                                // [NSL + 1] offsets into sval / scol
+  int* sbase = shal + HC;                                        // [NSL + 1] offsets into sval / scol
   int* sb0 = sbase + ((NSL + 4) & ~3);                           // [NSL] offsets into ss0, -1 = slice has no S0 entries
   unsigned short* scol = reinterpret_cast<unsigned short*>(sb0 + NSL);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -247,22 +257,28 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
     s_act[tid] = (rz > P.c->thr[tid]) ? 1 : 0;
   }
   for (int i = tid; i < NH * 2 * 32 * 2 * NVM; i += EP_T) s_prev[i] = 0ull;
-  for (int i = tid; i < R * B; i += EP_T) {
-    const size_t gidx = (size_t)lo * B + i;
-    const bool in = gidx < P.vec_len;
-    sp[i] = in ? P.z[gidx] : 0.0;                               // p_0 = z_0 (padding rows hold zeros)
-    const double d = in ? P.dg[gidx] : 0.0;
-    sdinv[i] = (d > 0.0) ? 1.0 / d : 0.0;
+  for (int i = tid; i < 2 * R; i += EP_T) {                      // (pair q, row): 16 contiguous bytes in global memory
+    const int q = i / R, row = i - q * R;
+    const size_t gidx = ((size_t)lo + row) * B + 2 * q;
+    double2 zv = make_double2(0.0, 0.0), dv = zv;
+    if (gidx < P.vec_len) {
+      zv = *reinterpret_cast<const double2*>(P.z + gidx);        // p_0 = z_0 (padding rows hold zeros)
+      dv = *reinterpret_cast<const double2*>(P.dg + gidx);
+    }
+    sp[(size_t)q * RH + row] = zv;
+    szo[(size_t)q * R + row] = zv;
+    sdinv[(size_t)q * R + row] = make_double2(dv.x > 0.0 ? 1.0 / dv.x : 0.0, dv.y > 0.0 ? 1.0 / dv.y : 0.0);
   }
   for (int h = tid; h < nh; h += EP_T) shal[h] = P.halo_idx[hp + h];
   __syncthreads();
-  for (int i = tid; i < nh * B; i += EP_T) {
-    const double zv = P.z[(size_t)shal[i >> LB] * B + (i & (B - 1))];
-    sp[R * B + i] = zv;
-    szh[i] = zv;
+  for (int i = tid; i < 2 * nh; i += EP_T) {
+    const int q = i / nh, h = i - q * nh;
+    const double2 zv = *reinterpret_cast<const double2*>(P.z + (size_t)shal[h] * B + 2 * q);
+    sp[(size_t)q * RH + R + h] = zv;
+    szh[(size_t)q * HC + h] = zv;
   }
   int wid[EP_RPT], base[EP_RPT], b0off[EP_RPT];
-  double x[EP_RPT][B], z[EP_RPT][B], wown[EP_RPT][B];
+  double x[EP_RPT][B];
   double mv[EP_RPT][EP_K];
   unsigned mc[EP_RPT][EP_K / 2];
   unsigned pubmask = 0u;
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
     base[k] = 0;
     b0off[k] = -1;
 #pragma unroll
-    for (int b = 0; b < B; ++b) x[k][b] = z[k][b] = wown[k][b] = 0.0;
+    for (int b = 0; b < B; ++b) x[k][b] = 0.0;
 #pragma unroll
     for (int kk = 0; kk < EP_K; ++kk) mv[k][kk] = 0.0;
 #pragma unroll
@@ -286,9 +302,10 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
       b0off[k] = sb0[sl];
       const size_t gi = ((size_t)s * 32 + lane) * B;
 #pragma unroll
-      for (int b = 0; b < B; ++b) {
-        x[k][b] = P.x[gi + b];
-        z[k][b] = sp[(size_t)(sl * 32 + lane) * B + b];
+      for (int q = 0; q < 2; ++q) {
+        const double2 xv = *reinterpret_cast<const double2*>(P.x + gi + 2 * q);
+        x[k][2 * q] = xv.x;
+        x[k][2 * q + 1] = xv.y;
       }
       if (P.pub[s * 32 + lane]) pubmask |= 1u << k;
 #pragma unroll
@@ -323,6 +340,7 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
     it[g] = 0;
     done[g] = s_ctl[g * 4 + 1] != 0;
   }
+  EP_PT_DECL
 
   // ---- phase 1 of half-tile g: t = A_b p on the own rows, w = t / d, publish, partial dot products, arrive
   auto phase1 = [&](const int g) {
@@ -342,76 +360,97 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
 #pragma unroll
           for (int kk = 0; kk < EP_K; ++kk) {
             const int c = (int)((mc[k][kk >> 1] >> (16 * (kk & 1))) & 0xffffu);
-            double pc[BG];
-            ep_gather<BG>(sp + (size_t)c * B + g * BG, pc);
 #pragma unroll
-            for (int bl = 0; bl < BG; ++bl) a[bl] = fma(mv[k][kk], pc[bl], a[bl]);
+            for (int ql = 0; ql < NPG; ++ql) {
+              const double2 pv = sp[(size_t)(g * NPG + ql) * RH + c];
+              a[2 * ql] = fma(mv[k][kk], pv.x, a[2 * ql]);
+              a[2 * ql + 1] = fma(mv[k][kk], pv.y, a[2 * ql + 1]);
+            }
           }
           for (int kk = 0; kk < ov; ++kk) {
             const double m = sval[bs + kk * 32];
-            double pc[BG];
-            ep_gather<BG>(sp + (size_t)scol[bs + kk * 32] * B + g * BG, pc);
+            const int c = scol[bs + kk * 32];
 #pragma unroll
-            for (int bl = 0; bl < BG; ++bl) a[bl] = fma(m, pc[bl], a[bl]);
+            for (int ql = 0; ql < NPG; ++ql) {
+              const double2 pv = sp[(size_t)(g * NPG + ql) * RH + c];
+              a[2 * ql] = fma(m, pv.x, a[2 * ql]);
+              a[2 * ql + 1] = fma(m, pv.y, a[2 * ql + 1]);
+            }
           }
         } else {
           const double* s0p = ss0 + b0off[k] + lane;
 #pragma unroll
           for (int kk = 0; kk < EP_K; ++kk) {
             const int c = (int)((mc[k][kk >> 1] >> (16 * (kk & 1))) & 0xffffu);
-            double pc[BG];
-            ep_gather<BG>(sp + (size_t)c * B + g * BG, pc);
             const double sv = (kk < wid[k]) ? s0p[kk * 32] : 0.0;
 #pragma unroll
-            for (int bl = 0; bl < BG; ++bl) a[bl] = fma(fma(s_ks[g * BG + bl], sv, mv[k][kk]), pc[bl], a[bl]);
+            for (int ql = 0; ql < NPG; ++ql) {
+              const double2 pv = sp[(size_t)(g * NPG + ql) * RH + c];
+              a[2 * ql] = fma(fma(s_ks[g * BG + 2 * ql], sv, mv[k][kk]), pv.x, a[2 * ql]);
+              a[2 * ql + 1] = fma(fma(s_ks[g * BG + 2 * ql + 1], sv, mv[k][kk]), pv.y, a[2 * ql + 1]);
+            }
           }
           for (int kk = 0; kk < ov; ++kk) {
             const double m = sval[bs + kk * 32], sv = s0p[(kk + EP_K) * 32];
-            double pc[BG];
-            ep_gather<BG>(sp + (size_t)scol[bs + kk * 32] * B + g * BG, pc);
+            const int c = scol[bs + kk * 32];
 #pragma unroll
-            for (int bl = 0; bl < BG; ++bl) a[bl] = fma(fma(s_ks[g * BG + bl], sv, m), pc[bl], a[bl]);
+            for (int ql = 0; ql < NPG; ++ql) {
+              const double2 pv = sp[(size_t)(g * NPG + ql) * RH + c];
+              a[2 * ql] = fma(fma(s_ks[g * BG + 2 * ql], sv, m), pv.x, a[2 * ql]);
+              a[2 * ql + 1] = fma(fma(s_ks[g * BG + 2 * ql + 1], sv, m), pv.y, a[2 * ql + 1]);
+            }
           }
         }
         const int i = (warp * EP_RPT + k) * 32 + lane;
 #pragma unroll
-        for (int bl = 0; bl < BG; ++bl) {
-          const int b = g * BG + bl;
-          const double t = a[bl];
-          const double w = t * sdinv[(size_t)i * B + b];
-          wown[k][b] = w;
-          if (pubmask & (1u << k)) hf_pkt_store(qout + (size_t)(lo + i) * B + b, w, gen[g]);
-          d[bl * 3 + 0] = fma(sp[(size_t)i * B + b], t, d[bl * 3 + 0]);
-          d[bl * 3 + 1] = fma(z[k][b], t, d[bl * 3 + 1]);
-          d[bl * 3 + 2] = fma(t, w, d[bl * 3 + 2]);
+        for (int ql = 0; ql < NPG; ++ql) {
+          const int q = g * NPG + ql;
+          const double2 di = sdinv[(size_t)q * R + i];
+          const double2 pv = sp[(size_t)q * RH + i], zv = szo[(size_t)q * R + i];
+          const double t0 = a[2 * ql], t1 = a[2 * ql + 1];
+          const double w0 = t0 * di.x, w1 = t1 * di.y;
+          swo[(size_t)q * R + i] = make_double2(w0, w1);
+          if (pubmask & (1u << k)) {
+            hf_pkt_store(qout + (size_t)(lo + i) * B + 2 * q, w0, gen[g]);
+            hf_pkt_store(qout + (size_t)(lo + i) * B + 2 * q + 1, w1, gen[g]);
+          }
+          d[(2 * ql) * 3 + 0] = fma(pv.x, t0, d[(2 * ql) * 3 + 0]);
+          d[(2 * ql) * 3 + 1] = fma(zv.x, t0, d[(2 * ql) * 3 + 1]);
+          d[(2 * ql) * 3 + 2] = fma(t0, w0, d[(2 * ql) * 3 + 2]);
+          d[(2 * ql + 1) * 3 + 0] = fma(pv.y, t1, d[(2 * ql + 1) * 3 + 0]);
+          d[(2 * ql + 1) * 3 + 1] = fma(zv.y, t1, d[(2 * ql + 1) * 3 + 1]);
+          d[(2 * ql + 1) * 3 + 2] = fma(t1, w1, d[(2 * ql + 1) * 3 + 2]);
         }
       }
     }
+    EP_PT_MARK(0);
     auto eb_of = [&](int bl, int j) {
       const int e_pp = hf_exp2(s_pp[g * BG + bl]), e_rr = hf_exp2(s_rz[g * BG + bl]);
       const int e = (j == 0) ? e_pp + 4 + HF_FX_MARGIN - P.eb_shift : (j == 1) ? (e_rr + e_pp + 1) / 2 + 5 + HF_FX_MARGIN : e_pp + 8 + HF_FX_MARGIN;
       return hf_clamp_exp(e);
     };
     ep_arrive<BG, 3>(d, eb_of, P.acc, g, gen[g], sred + g * (2 * EP_W * BG * NVM), P.fail);
+    EP_PT_MARK(1);
   };
 
   // ---- phase 2 of half-tile g: halo packets, wait for the sums, updates, direct residual check when due
   auto phase2 = [&](const int g) {
     const uint4* qin = P.qpk + (size_t)(it[g] & 1) * P.pk_stride;
     if (warp >= 1) {
-      constexpr int NP = EP_T - 32;
-      for (int h0 = tid - 32; h0 < nh * BG; h0 += 4 * NP) {
-        uint4 hq[4];
-        bool need[4];
-        size_t src[4];
-        int dst[4];
+      constexpr int NT = EP_T - 32;
+      constexpr int NF = (BG == 4) ? 5 : 3;                    // packets in flight per thread: one round covers ~280 halo rows
+      for (int h0 = tid - 32; h0 < nh * BG; h0 += NF * NT) {
+        uint4 hq[NF];
+        bool need[NF];
+        size_t src[NF];
+        int dst[NF];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int idx = h0 + t * NP;
+        for (int t = 0; t < NF; ++t) {
+          const int idx = h0 + t * NT;
           need[t] = idx < nh * BG;
-          const int h = need[t] ? idx / BG : 0, bl = need[t] ? idx % BG : 0;
-          src[t] = (size_t)shal[h] * B + g * BG + bl;
-          dst[t] = h * B + g * BG + bl;
+          const int h = need[t] ? idx / BG : 0, b = g * BG + (need[t] ? idx % BG : 0);
+          src[t] = (size_t)shal[h] * B + b;
+          dst[t] = ((b >> 1) * HC + h) * 2 + (b & 1);
         }
         bool pending;
         int spins = 0;
@@ -422,14 +461,14 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
             break;
           }
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
+          for (int t = 0; t < NF; ++t)
             if (need[t]) hq[t] = hf_pkt_load(qin + src[t]);
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
+          for (int t = 0; t < NF; ++t)
             if (need[t]) {
               if (hf_pkt_ok(hq[t], gen[g])) {
                 need[t] = false;
-                swh[dst[t]] = hf_pkt_val(hq[t]);
+                reinterpret_cast<double*>(swh)[dst[t]] = hf_pkt_val(hq[t]);
               } else {
                 pending = true;
               }
@@ -437,6 +476,7 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
         } while (pending);
       }
     }
+    EP_PT_MARK(2);
     auto eb3 = [&](int bl, int j) {
       const int e_pp = hf_exp2(s_pp[g * BG + bl]), e_rr = hf_exp2(s_rz[g * BG + bl]);
       const int e = (j == 0) ? e_pp + 4 + HF_FX_MARGIN - P.eb_shift : (j == 1) ? (e_rr + e_pp + 1) / 2 + 5 + HF_FX_MARGIN : e_pp + 8 + HF_FX_MARGIN;
@@ -457,10 +497,11 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
       const bool want = lane < BG && act && (since >= HF_RR_CHECK || !(rz_new > s_thr[b]) || rz_new < 1e-4 * s_ref[b]);
       const bool check = __any_sync(0xffffffffu, want);
       if (lane < BG) {
+        const double beta = (act && !check) ? rz_new / rz : 0.0;
         s_alpha[b] = alpha;
-        s_beta[b] = (act && !check) ? rz_new / rz : 0.0;
+        s_beta[b] = beta;
         if (!check) {
-          s_pp[b] = fma(s_beta[b] * s_beta[b], s_pp[b], fabs(rz_new));
+          s_pp[b] = fma(beta * beta, s_pp[b], fabs(rz_new));
           s_rz[b] = rz_new;
         }
       }
@@ -470,6 +511,7 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
       }
     }
     __syncthreads();
+    EP_PT_MARK(3);
     const bool check = s_ctl[g * 4 + 0] != 0;
     double al[BG], be[BG];
 #pragma unroll
@@ -485,24 +527,35 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
       if (wid[k] >= 0) {
         const int i = (warp * EP_RPT + k) * 32 + lane;
 #pragma unroll
-        for (int bl = 0; bl < BG; ++bl) {
-          const int b = g * BG + bl;
-          const double pv = sp[(size_t)i * B + b];
-          x[k][b] = fma(al[bl], pv, x[k][b]);
-          const double zv = fma(-al[bl], wown[k][b], z[k][b]);
-          z[k][b] = zv;
-          if (check) dd[bl] = fma(zv * P.dg[(size_t)(lo + i) * B + b], zv, dd[bl]);
-          else sp[(size_t)i * B + b] = fma(be[bl], pv, zv);
+        for (int ql = 0; ql < NPG; ++ql) {
+          const int q = g * NPG + ql;
+          const double2 pv = sp[(size_t)q * RH + i], wv = swo[(size_t)q * R + i], zo = szo[(size_t)q * R + i];
+          x[k][2 * q] = fma(al[2 * ql], pv.x, x[k][2 * q]);
+          x[k][2 * q + 1] = fma(al[2 * ql + 1], pv.y, x[k][2 * q + 1]);
+          const double z0 = fma(-al[2 * ql], wv.x, zo.x);
+          const double z1 = fma(-al[2 * ql + 1], wv.y, zo.y);
+          szo[(size_t)q * R + i] = make_double2(z0, z1);
+          if (check) {
+            const double2 dv = *reinterpret_cast<const double2*>(P.dg + (size_t)(lo + i) * B + 2 * q);
+            dd[2 * ql] = fma(z0 * dv.x, z0, dd[2 * ql]);
+            dd[2 * ql + 1] = fma(z1 * dv.y, z1, dd[2 * ql + 1]);
+          } else {
+            sp[(size_t)q * RH + i] = make_double2(fma(be[2 * ql], pv.x, z0), fma(be[2 * ql + 1], pv.y, z1));
+          }
         }
       }
     }
-    for (int idx = tid; idx < nh * BG; idx += EP_T) {
-      const int h = idx / BG, bl = idx % BG;
-      const int o = h * B + g * BG + bl;
-      const double a1 = s_alpha[g * BG + bl];
-      const double zv = fma(-a1, swh[o], szh[o]);
-      szh[o] = zv;
-      if (!check) sp[(size_t)R * B + o] = fma(s_beta[g * BG + bl], sp[(size_t)R * B + o], zv);
+    for (int idx = tid; idx < nh * NPG; idx += EP_T) {
+      const int ql = idx / nh, h = idx - ql * nh;
+      const int q = g * NPG + ql;
+      const double a0 = s_alpha[2 * q], a1 = s_alpha[2 * q + 1];
+      const double2 wv = swh[(size_t)q * HC + h], zo = szh[(size_t)q * HC + h];
+      const double2 zv = make_double2(fma(-a0, wv.x, zo.x), fma(-a1, wv.y, zo.y));
+      szh[(size_t)q * HC + h] = zv;
+      if (!check) {
+        const double2 pv = sp[(size_t)q * RH + R + h];
+        sp[(size_t)q * RH + R + h] = make_double2(fma(s_beta[2 * q], pv.x, zv.x), fma(s_beta[2 * q + 1], pv.y, zv.y));
+      }
     }
     ++it[g];
     if (check) {
@@ -540,20 +593,24 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
         if (wid[k] >= 0) {
           const int i = (warp * EP_RPT + k) * 32 + lane;
 #pragma unroll
-          for (int bl = 0; bl < BG; ++bl) {
-            const int b = g * BG + bl;
-            sp[(size_t)i * B + b] = fma(s_beta[b], sp[(size_t)i * B + b], z[k][b]);
+          for (int ql = 0; ql < NPG; ++ql) {
+            const int q = g * NPG + ql;
+            const double2 pv = sp[(size_t)q * RH + i], zv = szo[(size_t)q * R + i];
+            sp[(size_t)q * RH + i] = make_double2(fma(s_beta[2 * q], pv.x, zv.x), fma(s_beta[2 * q + 1], pv.y, zv.y));
           }
         }
       }
-      for (int idx = tid; idx < nh * BG; idx += EP_T) {
-        const int h = idx / BG, bl = idx % BG;
-        const int o = h * B + g * BG + bl;
-        sp[(size_t)R * B + o] = fma(s_beta[g * BG + bl], sp[(size_t)R * B + o], szh[o]);
+      for (int idx = tid; idx < nh * NPG; idx += EP_T) {
+        const int ql = idx / nh, h = idx - ql * nh;
+        const int q = g * NPG + ql;
+        const double2 pv = sp[(size_t)q * RH + R + h], zv = szh[(size_t)q * HC + h];
+        sp[(size_t)q * RH + R + h] = make_double2(fma(s_beta[2 * q], pv.x, zv.x), fma(s_beta[2 * q + 1], pv.y, zv.y));
       }
       done[g] = s_ctl[g * 4 + 1] != 0;
     }
+    EP_PT_MARK(4);
     __syncthreads();
+    EP_PT_MARK(5);
   };
 
   bool capped = false;
@@ -577,12 +634,13 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
     }
     if (all) break;
   }
+  EP_PT_STORE
 #pragma unroll
   for (int k = 0; k < EP_RPT; ++k)
     if (wid[k] >= 0) {
       const size_t gi = ((size_t)lo + (warp * EP_RPT + k) * 32 + lane) * B;
 #pragma unroll
-      for (int b = 0; b < B; ++b) P.x[gi + b] = x[k][b];
+      for (int q = 0; q < 2; ++q) *reinterpret_cast<double2*>(P.x + gi + 2 * q) = make_double2(x[k][2 * q], x[k][2 * q + 1]);
     }
   if (blockIdx.x == 0 && tid == 0) {
     int itmax = 0;
@@ -676,24 +734,19 @@ k_ens_rz(size_t total, const double* __restrict__ z, const double* __restrict__ 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-template <int LB, int NH>
+template <int NH>
 static size_t ep_smem_bytes(int mat_cap, int s0_cap, int halo_cap) {
-  constexpr int B = 1 << LB, BG = B / NH;
-  size_t dbl = (size_t)mat_cap + s0_cap + (size_t)(EP_R + halo_cap) * B + 2 * (size_t)halo_cap * B + (size_t)EP_R * B +
+  constexpr int B = 4, BG = B / NH;
+  size_t dbl = (size_t)mat_cap + s0_cap + (size_t)(EP_R + halo_cap) * B + 2 * (size_t)halo_cap * B + 3 * (size_t)EP_R * B +
                NH * 2 * EP_W * BG * 3 + 7 * B;
   size_t u64 = (size_t)NH * 2 * 32 * 2 * 3;
   size_t i32 = (size_t)B + NH * 4 + halo_cap + ((EP_R / 32 + 4) & ~3) + EP_R / 32;
   return dbl * 8 + u64 * 8 + i32 * 4 + (size_t)mat_cap * 2 + 16;
 }
 
-static const void* ep_kernel(int LB, int nh) {
-  if (LB == 2) return nh == 2 ? (const void*)k_ens_patch<2, 2> : (const void*)k_ens_patch<2, 1>;
-  if (LB == 1) return nh == 2 ? (const void*)k_ens_patch<1, 2> : (const void*)k_ens_patch<1, 1>;
-  return nullptr;
-}
-static size_t ep_bytes(int LB, int nh, int mat_cap, int s0_cap, int halo_cap) {
-  if (LB == 2) return nh == 2 ? ep_smem_bytes<2, 2>(mat_cap, s0_cap, halo_cap) : ep_smem_bytes<2, 1>(mat_cap, s0_cap, halo_cap);
-  return nh == 2 ? ep_smem_bytes<1, 2>(mat_cap, s0_cap, halo_cap) : ep_smem_bytes<1, 1>(mat_cap, s0_cap, halo_cap);
+static const void* ep_kernel(int nh) { return nh == 2 ? (const void*)k_ens_patch<2> : (const void*)k_ens_patch<1>; }
+static size_t ep_bytes(int nh, int mat_cap, int s0_cap, int halo_cap) {
+  return nh == 2 ? ep_smem_bytes<2>(mat_cap, s0_cap, halo_cap) : ep_smem_bytes<1>(mat_cap, s0_cap, halo_cap);
 }
 
 // Plans the on-chip kernel for the tile in `e` (called by hf_ens_create): needs the patch plan of the single-simulation
@@ -701,10 +754,10 @@ static size_t ep_bytes(int LB, int nh, int mat_cap, int s0_cap, int halo_cap) {
 int hf_ens_oc_plan(hf_ctx* c, EnsState* e) {
   e->oc_ok = false;
   if (getenv("HF_ENS_STREAM")) return HF_OK;                     // tuning / test knob: keep the streaming kernels
-  if (e->LB < 1 || e->LB > 2) return HF_OK;
+  if (e->LB != 2) return HF_OK;                                  // tiles of 4 variants (smaller tiles are padded to 4)
   SellOp& op = c->opA;
   if (!op.pp_rpt) HF_TRY(hf_patch_plan(c, op));
-  if (op.pp_rpt != EP_RPT || op.pp_grid > c->sm_count) return HF_OK;
+  if (op.pp_rpt * HF_PT != EP_R || op.pp_grid > c->sm_count) return HF_OK;   // same 1024-row patches as the single-simulation kernel
   const int nsl = op.nslices, B = e->B;
   e->oc_rows = (size_t)e->nchunks * (HF_EPAIRS / B);
   if ((size_t)op.pp_grid * EP_R > e->oc_rows + EP_R) return HF_OK;
@@ -739,15 +792,14 @@ int hf_ens_oc_plan(hf_ctx* c, EnsState* e) {
   s0_cap = (s0_cap + 7) & ~7;
   int max_smem = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
-  int nh = (B >= 2) ? 2 : 1;
+  int nh = 1;                                                    // measured: 7.2 us per iteration of the tile against 10.2 with two half-tiles
   if (const char* env = getenv("HF_ENS_NH")) nh = std::max(1, std::min(2, atoi(env)));
-  if ((1 << e->LB) / nh < 1) nh = 1;
-  const size_t bytes = ep_bytes(e->LB, nh, mat_cap, s0_cap, op.pp_halo_cap);
+  const size_t bytes = ep_bytes(nh, mat_cap, s0_cap, op.pp_halo_cap);
   if (bytes > (size_t)max_smem) return HF_OK;
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
   if (!coop) return HF_OK;
-  HF_CUDA(cudaFuncSetAttribute(ep_kernel(e->LB, nh), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  HF_CUDA(cudaFuncSetAttribute(ep_kernel(nh), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   e->oc_nh = nh;
   e->oc_grid = G;
   e->oc_mat_cap = mat_cap;
@@ -766,10 +818,7 @@ int hf_ens_oc_solve_async(hf_ctx* c, EnsState* e, int step_slot) {
   if (!e->oc_ok) return hf_fail(HF_ERR_STATE, "on-chip ensemble kernel is not planned for this tile");
   const SellOp& op = c->opA;
   const size_t total = e->oc_rows * e->B;
-  switch (e->LB) {
-    case 1: k_ens_rz<1><<<e->grid, HF_ET, 0, c->stream>>>(total, e->z.p, e->dg.p, e->part.p, e->ctrl.p); break;
-    default: k_ens_rz<2><<<e->grid, HF_ET, 0, c->stream>>>(total, e->z.p, e->dg.p, e->part.p, e->ctrl.p); break;
-  }
+  k_ens_rz<2><<<e->grid, HF_ET, 0, c->stream>>>(total, e->z.p, e->dg.p, e->part.p, e->ctrl.p);
   HF_CUDA(cudaGetLastError());
   HF_CUDA(cudaMemsetAsync(e->oc_acc.p, 0, e->oc_acc.n * sizeof(unsigned long long), c->stream));
   EnsOcArgs a;
@@ -798,9 +847,10 @@ int hf_ens_oc_solve_async(hf_ctx* c, EnsState* e, int step_slot) {
   a.acc = e->oc_acc.p;
   a.iters_out = (step_slot >= 0 && (size_t)step_slot < e->oc_iters.n) ? e->oc_iters.p + step_slot : nullptr;
   a.fail = e->oc_fail.p;
+  a.phase = c->debug_phase.n ? c->debug_phase.p : nullptr;
   void* args[] = {&a};
-  HF_CUDA(cudaFuncSetAttribute(ep_kernel(e->LB, e->oc_nh), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->oc_smem));
-  HF_CUDA(cudaLaunchCooperativeKernel(ep_kernel(e->LB, e->oc_nh), dim3(e->oc_grid), dim3(EP_T), args, e->oc_smem, c->stream));
+  HF_CUDA(cudaFuncSetAttribute(ep_kernel(e->oc_nh), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->oc_smem));
+  HF_CUDA(cudaLaunchCooperativeKernel(ep_kernel(e->oc_nh), dim3(e->oc_grid), dim3(EP_T), args, e->oc_smem, c->stream));
   c->stat_launches += 2;
   return HF_OK;
 }

@@ -26,11 +26,13 @@ for uniform in (True, False):
         t0 = time.time(); s.ens_destroy(); t_destroy = time.time() - t0
         s.set_state(np.full(n, c.ic))
         t0 = time.time(); s.ens_create(ks, cf, tag); t_create2 = time.time() - t0
+        s.set_profile(True)
         t0 = time.time()
         hist, iters = s.ens_run(c.amps[:steps], c.ic, [0, n // 2])
         wall = time.time() - t0
         ms = s.stats()["run_ms"]
+        solve_ms, _ = s.solve_profile()
         print(f"N={n} B={B} uniform_k={uniform} {env} path={path}: create {t_create*1e3:.1f}/{t_create2*1e3:.1f} ms destroy {t_destroy*1e3:.1f} ms; "
               f"{steps} steps dev {ms:.1f} ms wall {wall*1e3:.1f} ms, iterations {int(iters.sum())} -> {ms/B:.2f} ms/sim, "
-              f"{B/(wall+t_create2+t_destroy):.1f} sims/s incl. create/destroy, {ms*1e3/max(1,iters.sum()):.2f} us/iteration (all incl.)", flush=True)
+              f"{B/(wall+t_create2+t_destroy):.1f} sims/s incl. create/destroy, {ms*1e3/max(1,iters.sum()):.2f} us/iteration (all incl.), solves {solve_ms:.1f} ms = {solve_ms*1e3/max(1,iters.sum()):.2f} us/iteration", flush=True)
         s.close()
