@@ -10,6 +10,8 @@ stand-ins (``Domain``, ``MeshTags``) that expose what the runners read:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .materials import Material  # noqa: F401  (re-export, like the reference's star imports)
@@ -107,9 +109,18 @@ class Mesh:
             raise RuntimeError("Mesh not built – call build_mesh() first.")
         return Domain(self.mesh), MeshTags(self.mesh.cell_tag), MeshTags(np.zeros(0, np.int32), dim=1)
 
+    _msh_cache = {}          # (path, mtime, size) -> parsed arrays: a sweep loads the same file for several contexts
+
     @staticmethod
     def msh_to_dolfinx(filename: str, *, comm=COMM, gdim: int = 2, rank: int = 0):
-        nodes, tris, tag, _ = read_msh(filename)
+        st = os.stat(filename)
+        key = (os.path.abspath(filename), st.st_mtime_ns, st.st_size)
+        hit = Mesh._msh_cache.get(key)
+        if hit is None:
+            nodes, tris, tag, _ = read_msh(filename)
+            Mesh._msh_cache.clear()                               # one mesh at a time is enough (width groups come in turn)
+            Mesh._msh_cache[key] = hit = (nodes, tris, tag)
+        nodes, tris, tag = (a.copy() for a in hit)
         arrays = MeshArrays(nodes, tris, tag)
         return Domain(arrays), MeshTags(arrays.cell_tag), MeshTags(np.zeros(0, np.int32), dim=1)
 

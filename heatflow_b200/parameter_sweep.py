@@ -32,6 +32,7 @@ import json
 import multiprocessing as mp
 import os
 import queue
+import sys
 import threading
 import time
 from datetime import datetime
@@ -188,11 +189,16 @@ class _OutputWriter:
 
 
 def _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine="auto",
-                     output_dir=None, names=None):
+                     output_dir=None, names=None, share=None):
     """Set the group's mesh up on ``device``, run this rank's tiles and (``output_dir`` given) write their run
-    folders.  Returns (idx, hist, iters, secs, errors, step_times)."""
+    folders.  Returns (idx, hist, iters, secs, errors, step_times).  ``share`` = (rank, world): when the serial
+    engine runs the group, the rank takes every world-th variant of the k-sorted list instead of its tiles - tiles
+    of 16 cut a conductivity's heating widths into a narrow and a wide half, and the wide halves (more PCG
+    iterations) all land on the odd ranks (measured: 17.7 s against 19.7 s on two GPUs)."""
     cfg0 = modify_config_for_parameters(base_config, combinations[0]['fwhm'], combinations[0]['k'], combinations[0]['width'])
     _, stack = _runner_for(cfg0)
+    t_setup = time.time()
+    timing = bool(os.environ.get("HF_SWEEP_TIMING"))
     with suppress_output(suppress_print):
         sim = Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device)
     extra = []
@@ -211,14 +217,22 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
         watch = sim.watcher_nodes(list(get_watcher_points(cfg0).values()))
         fwhm = np.array([c['fwhm'] for c in combinations])
         k = np.array([c['k'] for c in combinations])
+        if share is not None and (engine == "serial" or (engine == "auto" and sim.solver.on_chip())):
+            tiles = [np.argsort(k, kind="stable")[share[0]::share[1]]]
+            n_mine = len(tiles[0])
         if output_dir is not None:
             writer = _OutputWriter(output_dir, base_config, combinations, sim.step_t.copy(), names)
+        t_run = time.time()
         idx, hist, iters, secs, errors = sweep.run_tiles(sim, fwhm, k, tiles, watch, engine=engine, extra_sims=extra,
                                                          on_done=writer.submit if writer else None)
+        t_write = time.time()
         if writer is not None:
             errors = dict(errors)
             errors.update(writer.close())
             writer = None
+        if timing:
+            print(f"[sweep timing] device {device}: set-up {t_run - t_setup:.2f}s, {n_mine} simulations {t_write - t_run:.2f}s, "
+                  f"output drain {time.time() - t_write:.2f}s", file=sys.stderr, flush=True)
         return idx, hist, iters, secs, errors, sim.step_t.copy()
     finally:
         if writer is not None:
@@ -228,16 +242,44 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
             e.close()
 
 
-def _rank_share(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine, output_dir, names):
+def _rank_share(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine, output_dir, names,
+                share=None):
     """``_group_on_device`` that never raises: a failure outside the per-variant handlers (set-up, out of memory)
     marks every variant of this rank as failed, so that the rank still takes part in the final gather."""
     mine = np.concatenate([np.asarray(t, dtype=np.int64) for t in tiles]) if len(tiles) else np.zeros(0, np.int64)
     try:
         idx, _hist, iters, secs, errors, _ = _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles,
-                                                            suppress_print, engine, output_dir, names)
+                                                            suppress_print, engine, output_dir, names, share=share)
         return idx, iters, secs, errors
     except Exception as exc:
         return mine, np.full(len(mine), -1, dtype=np.int64), np.zeros(len(mine)), {int(i): str(exc) for i in mine}
+
+
+def _wait_for_mesh(mesh_folder, mesh_file, mesh_cfg_file, timeout_s=7200.0):
+    """Ranks > 0: block until rank 0 has marked the group's mesh files complete (``.mesh_ready``)."""
+    marker = os.path.join(mesh_folder, '.mesh_ready')
+    t0 = time.time()
+    while not (os.path.exists(marker) and os.path.exists(mesh_file) and os.path.exists(mesh_cfg_file)):
+        if time.time() - t0 > timeout_s:
+            raise TimeoutError(f"mesh files of rank 0 did not appear in {mesh_folder} within {timeout_s:.0f} s")
+        time.sleep(0.02)
+
+
+def _warm_up_collectives(local_rank):
+    """First use of a NCCL communicator costs ~1.3 s (measured): do it on a side thread while the sweep runs, so the
+    final gather - the sweep's one data-carrying collective - finds it ready."""
+    def work():
+        try:
+            import torch
+            import torch.distributed as dist
+            if dist.get_backend() == "nccl":
+                torch.cuda.set_device(local_rank)
+            dist.barrier()
+        except Exception:
+            pass                                     # the gather itself will report a broken process group
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    return t
 
 
 def _device_worker(args):
@@ -328,6 +370,7 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
     my_idx, my_iters, my_secs, my_errors = [], [], [], {}
     group_offset, offset = [], 0
     t_sweep = time.time()
+    warm = _warm_up_collectives(local_rank) if (world > 1 and mode != "per_run") else None
     for width_idx, (width, combinations) in enumerate(width_groups.items()):
         say(f"\nProcessing width group {width_idx + 1}/{len(width_groups)}: width = {width:.2e} m")
         say(f"  {len(combinations)} runs for this width")
@@ -337,6 +380,8 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
         if rank == 0:
             os.makedirs(mesh_folder, exist_ok=True)
             if not (os.path.exists(mesh_file) and os.path.exists(mesh_cfg_file)):
+                if os.path.exists(os.path.join(mesh_folder, '.mesh_ready')):
+                    os.remove(os.path.join(mesh_folder, '.mesh_ready'))
                 say(f"  Building new mesh for width {width:.2e} m")
                 config = modify_config_for_parameters(base_config, combinations[0]['fwhm'], combinations[0]['k'], width)
                 _, stack = _runner_for(config)
@@ -345,11 +390,14 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
                     prepare_mesh(config, stack, mesh_folder, rebuild_mesh=True)
             else:
                 say(f"  Reusing existing mesh for width {width:.2e} m")
-        if world > 1:
-            # the other ranks wait for the mesh files of rank 0 (no data moves), then every rank loads the mesh and
-            # sets its device up concurrently
-            import torch.distributed as dist
-            dist.barrier()
+            with open(os.path.join(mesh_folder, '.mesh_ready'), 'w') as f:      # both files are complete
+                f.write("ok\n")
+        elif world > 1:
+            # the other ranks wait for rank 0's mesh files through the file system - no collective, so the NCCL
+            # communicator is set up in the background (below) while the devices are already working
+            _wait_for_mesh(mesh_folder, mesh_file, mesh_cfg_file)
+        if os.environ.get("HF_SWEEP_TIMING"):
+            print(f"[sweep timing] rank {rank}: mesh ready after {time.time() - t_sweep:.2f}s", file=sys.stderr, flush=True)
 
         if mode == "per_run":
             # the reference's own scheme: one run_simulation per parameter set (this rank's share)
@@ -374,15 +422,15 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
         t_group = time.time()
         if world > 1 or n_workers == 1:
             parts = [_rank_share(base_config, combinations, mesh_folder, batch, local_rank if world > 1 else 0, tiles[rank],
-                                 suppress_print, mode, output_dir, names)]
+                                 suppress_print, mode, output_dir, names, (rank, world) if world > 1 else None)]
         else:
             if mp.get_start_method(allow_none=True) != 'spawn':
                 try:
                     mp.set_start_method('spawn', force=True)
                 except RuntimeError:
                     pass
-            jobs = [(base_config, combinations, mesh_folder, batch, d, tiles[d], suppress_print, mode, output_dir, names)
-                    for d in range(n_workers)]
+            jobs = [(base_config, combinations, mesh_folder, batch, d, tiles[d], suppress_print, mode, output_dir, names,
+                     (d, n_workers)) for d in range(n_workers)]
             with mp.Pool(processes=n_workers, initializer=initialize_worker) as pool:
                 parts = pool.map(_device_worker, jobs)
         for idx_p, it_p, sec_p, err_p in parts:
@@ -395,6 +443,8 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
         offset += len(combinations)
 
     if mode != "per_run":
+        if warm is not None:
+            warm.join()
         cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
         gathered = sweep.gather_results(offset, 0, 0, cat(my_idx, np.int64), None, cat(my_iters, np.int64),
                                         cat(my_secs, np.float64), my_errors)       # the single collective of the sweep
@@ -415,6 +465,8 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
                         results.append(result)
                     _report(say, result, total_completed, len(parameter_combinations))
             say(f"\nall groups finished in {time.time() - t_sweep:.2f}s")
+    if os.environ.get("HF_SWEEP_TIMING"):
+        print(f"[sweep timing] rank {rank}: gather + summary done after {time.time() - t_sweep:.2f}s", file=sys.stderr, flush=True)
 
     if rank != 0:
         return [], []
@@ -437,6 +489,9 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
         total_runtime = sum(r['runtime'] for r in results)
         print(f"Average runtime per simulation: {avg_runtime:.2f}s")
         print(f"Total simulation time: {total_runtime:.2f}s")
+    wall = time.time() - t_sweep
+    print(f"Sweep wall time: {wall:.2f}s ({len(parameter_combinations) / max(wall, 1e-9):.2f} simulations/s on "
+          f"{world if world > 1 else n_workers} GPU(s), mesh handling, run folders and the final gather included)")
     return results, failed_runs
 
 

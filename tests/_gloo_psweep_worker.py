@@ -27,9 +27,9 @@ def fake_hist(combo, S):
 
 
 def fake_group(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine="auto", output_dir=None,
-               names=None):
+               names=None, share=None):
     rank = dist.get_rank()
-    assert os.path.isfile(os.path.join(mesh_folder, "mesh.msh"))         # rank 0 built it before the barrier
+    assert os.path.isfile(os.path.join(mesh_folder, "mesh.msh"))         # rank 0 built it and marked it ready
     if STATE["fail_rank"] == rank:
         raise RuntimeError(f"device lost on rank {rank}")
     S = int(base_config["timing"]["num_steps"])

@@ -182,3 +182,18 @@ def test_serial_engine_queue_results_and_errors(workers):
     # empty share
     out = sweep.run_tiles_serial(sims, fwhm, k, [], [4, 9])
     assert out[0].size == 0 and out[1].shape == (0, 5, 2)
+
+
+def test_serial_engine_share_is_a_partition_with_every_conductivity_on_every_rank():
+    # _group_on_device(share=(rank, world)): the serial engine deals the k-sorted variants one by one, so every rank
+    # sees every conductivity with a mix of narrow and wide heating profiles (tiles of 16 put all wide ones on odd ranks)
+    fw, ks = np.logspace(-6, -4, 32), np.logspace(0, 2, 32)
+    k = np.array([kk for f in fw for kk in ks])
+    f = np.array([ff for ff in fw for _ in ks])
+    order = np.argsort(k, kind="stable")
+    shares = [order[r::4] for r in range(4)]
+    assert sorted(np.concatenate(shares).tolist()) == list(range(len(k)))
+    means = [np.log(f[s]).mean() for s in shares]
+    assert max(means) - min(means) < 0.2                       # tiles of 16: the difference is ln(10) = 2.3
+    for s in shares:
+        assert len(np.unique(k[s])) == 32
