@@ -189,7 +189,7 @@ class _OutputWriter:
 
 
 def _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine="auto",
-                     output_dir=None, names=None, share=None):
+                     output_dir=None, names=None, share=None, on_ready=None):
     """Set the group's mesh up on ``device``, run this rank's tiles and (``output_dir`` given) write their run
     folders.  Returns (idx, hist, iters, secs, errors, step_times).  ``share`` = (rank, world): when the serial
     engine runs the group, the rank takes every world-th variant of the k-sorted list instead of its tiles - tiles
@@ -218,11 +218,13 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
         fwhm = np.array([c['fwhm'] for c in combinations])
         k = np.array([c['k'] for c in combinations])
         if share is not None and (engine == "serial" or (engine == "auto" and sim.solver.on_chip())):
-            tiles = [np.argsort(k, kind="stable")[share[0]::share[1]]]
+            tiles = [serial_share(k, share[0], share[1])]
             n_mine = len(tiles[0])
         if output_dir is not None:
             writer = _OutputWriter(output_dir, base_config, combinations, sim.step_t.copy(), names)
         t_run = time.time()
+        if on_ready is not None:
+            on_ready()                                  # multi-rank sweeps: NCCL warm-up overlapping the first simulations
         idx, hist, iters, secs, errors = sweep.run_tiles(sim, fwhm, k, tiles, watch, engine=engine, extra_sims=extra,
                                                          on_done=writer.submit if writer else None)
         t_write = time.time()
@@ -242,17 +244,39 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
             e.close()
 
 
+def serial_share(k_values, rank, world):
+    """Variants of ``rank`` for the serial engine: position p of the k-sorted list goes to rank (p + p // world) % world
+    - one variant per rank out of every ``world`` consecutive ones, the offset rotating so that no rank always gets
+    the widest heating profile of its group."""
+    order = np.argsort(np.asarray(k_values, dtype=np.float64), kind="stable")
+    pos = np.arange(len(order))
+    return order[(pos + pos // world) % world == rank]
+
+
 def _rank_share(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine, output_dir, names,
                 share=None):
     """``_group_on_device`` that never raises: a failure outside the per-variant handlers (set-up, out of memory)
     marks every variant of this rank as failed, so that the rank still takes part in the final gather."""
     mine = np.concatenate([np.asarray(t, dtype=np.int64) for t in tiles]) if len(tiles) else np.zeros(0, np.int64)
+    warm = []
+
+    def on_ready():
+        warm.append(_warm_up_collectives(device))
+
     try:
         idx, _hist, iters, secs, errors, _ = _group_on_device(base_config, combinations, mesh_folder, batch, device, tiles,
-                                                            suppress_print, engine, output_dir, names, share=share)
+                                                            suppress_print, engine, output_dir, names, share=share,
+                                                            on_ready=on_ready if share is not None else None)
         return idx, iters, secs, errors
     except Exception as exc:
+        if share is not None:
+            mine = serial_share([c['k'] for c in combinations], share[0], share[1]) if engine == "serial" else mine
         return mine, np.full(len(mine), -1, dtype=np.int64), np.zeros(len(mine)), {int(i): str(exc) for i in mine}
+    finally:
+        if share is not None:
+            if not warm:                                # set-up failed before the warm-up: every rank still takes part
+                on_ready()
+            warm[0].join()
 
 
 def _wait_for_mesh(mesh_folder, mesh_file, mesh_cfg_file, timeout_s=7200.0):
@@ -266,12 +290,15 @@ def _wait_for_mesh(mesh_folder, mesh_file, mesh_cfg_file, timeout_s=7200.0):
 
 
 def _warm_up_collectives(local_rank):
-    """First use of a NCCL communicator costs ~1.3 s (measured): do it on a side thread while the sweep runs, so the
-    final gather - the sweep's one data-carrying collective - finds it ready."""
+    """First use of a NCCL communicator costs ~1.3 s (measured): do it on a side thread while the first simulations
+    run, so the final gather - the sweep's one data-carrying collective - finds it ready.  (Started during the device
+    set-up instead, it slowed that down from 0.6 s to 3.6 s.)"""
     def work():
         try:
             import torch
             import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                return                               # spawned workers without a process group: nothing to warm up
             if dist.get_backend() == "nccl":
                 torch.cuda.set_device(local_rank)
             dist.barrier()
@@ -370,7 +397,7 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
     my_idx, my_iters, my_secs, my_errors = [], [], [], {}
     group_offset, offset = [], 0
     t_sweep = time.time()
-    warm = _warm_up_collectives(local_rank) if (world > 1 and mode != "per_run") else None
+    warm = None
     for width_idx, (width, combinations) in enumerate(width_groups.items()):
         say(f"\nProcessing width group {width_idx + 1}/{len(width_groups)}: width = {width:.2e} m")
         say(f"  {len(combinations)} runs for this width")
@@ -443,8 +470,6 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
         offset += len(combinations)
 
     if mode != "per_run":
-        if warm is not None:
-            warm.join()
         cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
         gathered = sweep.gather_results(offset, 0, 0, cat(my_idx, np.int64), None, cat(my_iters, np.int64),
                                         cat(my_secs, np.float64), my_errors)       # the single collective of the sweep

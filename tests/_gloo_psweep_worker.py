@@ -27,7 +27,7 @@ def fake_hist(combo, S):
 
 
 def fake_group(base_config, combinations, mesh_folder, batch, device, tiles, suppress_print, engine="auto", output_dir=None,
-               names=None, share=None):
+               names=None, share=None, on_ready=None):
     rank = dist.get_rank()
     assert os.path.isfile(os.path.join(mesh_folder, "mesh.msh"))         # rank 0 built it and marked it ready
     if STATE["fail_rank"] == rank:

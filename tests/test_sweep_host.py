@@ -190,8 +190,8 @@ def test_serial_engine_share_is_a_partition_with_every_conductivity_on_every_ran
     fw, ks = np.logspace(-6, -4, 32), np.logspace(0, 2, 32)
     k = np.array([kk for f in fw for kk in ks])
     f = np.array([ff for ff in fw for _ in ks])
-    order = np.argsort(k, kind="stable")
-    shares = [order[r::4] for r in range(4)]
+    from heatflow_b200.parameter_sweep import serial_share
+    shares = [serial_share(k, r, 4) for r in range(4)]
     assert sorted(np.concatenate(shares).tolist()) == list(range(len(k)))
     means = [np.log(f[s]).mean() for s in shares]
     assert max(means) - min(means) < 0.2                       # tiles of 16: the difference is ln(10) = 2.3
