@@ -4,7 +4,12 @@
 
 #define HF_EB 32            // max variants per tile
 #define HF_ET 256           // threads per CTA of the set-up kernels
-#define HF_ENT 512          // threads per CTA of the iteration kernel
+#ifndef HF_ENT
+#define HF_ENT 256          // threads per CTA of the iteration kernel
+#endif
+#ifndef HF_EMINB
+#define HF_EMINB 2           // its CTAs per SM (measured at 1.15 M dofs, B = 16: 394 us per iteration with 512 x 1, 346 with 256 x 2, 355 with 256 x 3)
+#endif
 #define HF_EPAIRS 1024      // (row, variant) pairs per chunk: R = HF_EPAIRS / B rows
 #define HF_ERPT (HF_EPAIRS / HF_ENT)
 #define HF_EHPT 4           // halo pairs per thread carried in registers
@@ -24,6 +29,7 @@ struct EnsState {
   DevBuf<double> base0, s0;           // [nnz]
   DevBuf<double> ks, coeff;           // [B]
   DevBuf<double> dg, g, u, uprev, x, z, z1, p0, p1, w, w1;   // [Nalloc*B]; dg = diagonal of A_b (0 on Dirichlet rows)
+  DevBuf<double> drow;                // [2][rows]: base0_ii and S0_ii per row (0 on Dirichlet rows), d_ib = base0_ii + k_b S0_ii
   bool have_prev = false;
   DevBuf<double> part;                // [4][CTAs][B]
   // patch decomposition for the iteration kernel
@@ -52,6 +58,7 @@ struct EnsState {
   DevBuf<unsigned long long> oc_acc;  // fixed-point accumulators of the grid reductions (zeroed before every solve)
   DevBuf<uint4> oc_qpk;               // [2][rows * B] w = D^-1 A p exchange packets
   DevBuf<int> oc_iters, oc_fail;      // per-step iteration counts, failed solves
+  DevBuf<unsigned> oc_gen;            // [2] packet generation per half-tile, carried from launch to launch
   DevBuf<double> oc_u0;               // [2][rows * B] u, uprev at the start of hf_ens_run (repeat on the streaming kernels)
   ~EnsState() {
     for (auto& g : chunk_exec)

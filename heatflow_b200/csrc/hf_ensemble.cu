@@ -89,19 +89,30 @@ template <int LB>
 __global__ void __launch_bounds__(HF_ET)
 k_ens_diag(int N, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ base0,
            const double* __restrict__ s0, const unsigned char* __restrict__ bcflag, const double* __restrict__ ks,
-           double* __restrict__ dg, int* __restrict__ bad) {
+           double* __restrict__ dg, double* __restrict__ drow /*[2][rows]: base0_ii, S0_ii (0 on Dirichlet rows)*/, size_t rows,
+           int* __restrict__ bad) {
   constexpr int B = 1 << LB;
   const size_t idx = (size_t)blockIdx.x * HF_ET + threadIdx.x;
   const int i = (int)(idx >> LB), b = (int)(idx & (B - 1));
   if (i >= N) return;
-  double d = 0.0;
+  double d = 0.0, db = 0.0, ds = 0.0;
   if (!bcflag[i]) {
     for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
-      if (col[k] == i) d = fma(ks[b], s0[k], base0[k]);
+      if (col[k] == i) {
+        db = base0[k];
+        ds = s0[k];
+      }
+    d = fma(ks[b], ds, db);                    // the iteration kernel recomputes exactly this from drow
     if (!(d > 0.0)) {
       atomicExch(bad, i + 1);
       d = 1.0;
+      db = 1.0;
+      ds = 0.0;
     }
+  }
+  if (b == 0) {
+    drow[i] = db;
+    drow[rows + i] = ds;
   }
   dg[idx] = d;
 }
@@ -228,8 +239,8 @@ struct EnsPatch {
 //   bs[mcap] double2 | x[EP] | z[EP] | w[EP] | d[EP] | p[EP] | halo p[halo_cap*B] | lcol[mcap] u16 | rowptr[R+4] i32
 template <int LB>
 __device__ __forceinline__ void ens_issue_chunk(const EnsPatch& P, int ch, int k0, int k1, int lc0, unsigned char* st,
-                                                const double* x, const double* zo, const double* wo, const double* dg,
-                                                const double* po, unsigned long long* bar) {
+                                                const double* x, const double* zo, const double* wo, const double* drow,
+                                                size_t rows, const double* po, unsigned long long* bar) {
   constexpr int B = 1 << LB;
   constexpr int R = HF_EPAIRS / B;
   constexpr unsigned vb = HF_EPAIRS * 8u;
@@ -242,13 +253,14 @@ __device__ __forceinline__ void ens_issue_chunk(const EnsPatch& P, int ch, int k
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was last touched by ordinary loads/stores
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ens_smem_u32(bar)),
-               "r"(n * 16u + ncol * 2u + 5u * vb + (R + 4) * 4u)
+               "r"(n * 16u + ncol * 2u + 4u * vb + 2u * R * 8u + (R + 4) * 4u)
                : "memory");
   const size_t lo = (size_t)ch * HF_EPAIRS;
   ens_bulk(sx, x + lo, vb, bar, keep);
   ens_bulk(sx + vb, zo + lo, vb, bar, keep);
   ens_bulk(sx + 2 * vb, wo + lo, vb, bar, keep);
-  ens_bulk(sx + 3 * vb, dg + lo, vb, bar, keep);
+  ens_bulk(sx + 3 * vb, drow + (size_t)ch * R, R * 8u, bar, keep);              // base0_ii of the chunk's rows
+  ens_bulk(sx + 3 * vb + R * 8u, drow + rows + (size_t)ch * R, R * 8u, bar, keep);   // S0_ii
   ens_bulk(sx + 4 * vb, po + lo, vb, bar, keep);
   ens_bulk(srow, P.rowptr_pad + (size_t)ch * R, (R + 4) * 4u, bar, keep);
   if (ncol) ens_bulk(slc, P.lcol + lc0, ncol * 2u, bar, keep);
@@ -257,8 +269,8 @@ __device__ __forceinline__ void ens_issue_chunk(const EnsPatch& P, int ch, int k
 }
 
 template <int LB>
-__global__ void __launch_bounds__(HF_ENT, 1)
-k_ens_iter(EnsPatch P, int par, const double* __restrict__ ks, const double* __restrict__ dg, double* __restrict__ x,
+__global__ void __launch_bounds__(HF_ENT, HF_EMINB)
+k_ens_iter(EnsPatch P, int par, const double* __restrict__ ks, const double* __restrict__ drow, size_t rows, double* __restrict__ x,
            double* __restrict__ zb0, double* __restrict__ zb1, double* __restrict__ pb0, double* __restrict__ pb1,
            double* __restrict__ wb0, double* __restrict__ wb1, double* __restrict__ part, EnsCtrl* __restrict__ c) {
   constexpr int B = 1 << LB;
@@ -305,7 +317,7 @@ k_ens_iter(EnsPatch P, int par, const double* __restrict__ ks, const double* __r
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j < min(P.nstages, nloc))
-          ens_issue_chunk<LB>(P, blockIdx.x + j * G, e0[j], e1[j], el[j], smraw + (size_t)j * P.stage_bytes, x, zo, wo, dg, po,
+          ens_issue_chunk<LB>(P, blockIdx.x + j * G, e0[j], e1[j], el[j], smraw + (size_t)j * P.stage_bytes, x, zo, wo, drow, rows, po,
                               &full[j]);
     }
   }
@@ -375,7 +387,7 @@ k_ens_iter(EnsPatch P, int par, const double* __restrict__ ks, const double* __r
 #pragma unroll
     for (int t = 0; t < HF_ERPT; ++t) {
       const int i = t * HF_ENT + tid;
-      const double d = sd[i];
+      const double d = fma(kb, sd[R + (i >> LB)], sd[i >> LB]);   // diagonal of A_b from the row's (base0_ii, S0_ii): 16 B per row instead of 8 B per pair
       dinv[t] = (d > 0.0) ? __drcp_rn(d) : 0.0;
       double z_new = sz[i], p_new = z_new;
       if (it > 0) {
@@ -453,7 +465,7 @@ k_ens_iter(EnsPatch P, int par, const double* __restrict__ ks, const double* __r
     }
     __syncthreads();                    // the stage is free again
     if (tid == 0 && j + P.nstages < nloc)
-      ens_issue_chunk<LB>(P, ch + P.nstages * G, nx_k0, nx_k1, nx_lc, st, x, zo, wo, dg, po, &full[stg]);
+      ens_issue_chunk<LB>(P, ch + P.nstages * G, nx_k0, nx_k1, nx_lc, st, x, zo, wo, drow, rows, po, &full[stg]);
   }
   // ---- per-CTA, per-variant partials; the last CTA finalises the iteration
   const size_t GB = (size_t)G * B;
@@ -763,9 +775,10 @@ extern "C" int hf_ens_create(hf_ctx* c, int32_t batch, const double* k_sample, c
   HF_TRY(ens_assemble(c, sample_tag, 0.0, 0.0, c->dt, e->s0.p));
   for (DevBuf<double>* v : {&e->dg, &e->g, &e->u, &e->uprev, &e->x, &e->z, &e->z1, &e->p0, &e->p1, &e->w, &e->w1})
     HF_TRY(v->alloc(nb, c->stream));
+  HF_TRY(e->drow.alloc((size_t)2 * e->nchunks * e->R, c->stream));
   const size_t blocks = ((size_t)N * B + HF_ET - 1) / HF_ET;
   e->grid = (int)std::max<size_t>(1, std::min<size_t>(blocks, (size_t)c->sm_count * 8));
-  e->igrid = std::min(e->nchunks, c->sm_count);
+  e->igrid = std::min(e->nchunks, c->sm_count * HF_EMINB);
   HF_TRY(e->part.alloc((size_t)4 * std::max(e->grid, e->igrid) * B, c->stream));
   // ---- patch decomposition: halo lists, chunk-padded local columns, padded row pointers
   {
@@ -800,7 +813,10 @@ extern "C" int hf_ens_create(hf_ctx* c, int32_t batch, const double* k_sample, c
                      ~(size_t)127;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
-    const size_t avail = (size_t)max_smem - 8 * 1024;    // static shared memory of the kernel
+    int per_sm = 0;
+    cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device);
+    // HF_EMINB co-resident CTAs share the SM (1 KB per CTA is reserved by the system); 8 KB static shared memory
+    const size_t avail = std::min<size_t>((size_t)max_smem, (size_t)per_sm / HF_EMINB - 1024) - 8 * 1024;
     e->nstages = (int)std::min<size_t>(4, avail / e->stage_bytes);
     if (const char* env = getenv("HF_STAGES")) e->nstages = std::max(1, std::min(e->nstages, atoi(env)));
     if (e->nstages < 1)
@@ -814,7 +830,8 @@ extern "C" int hf_ens_create(hf_ctx* c, int32_t batch, const double* k_sample, c
   DevBuf<int> bad;
   HF_TRY(bad.alloc(1, c->stream));
   ENS_DISPATCH(e->LB, k_ens_diag<LB><<<(unsigned)blocks, HF_ET, 0, c->stream>>>(N, c->rowptr.p, c->col.p, e->base0.p, e->s0.p,
-                                                                                c->bcflag.p, e->ks.p, e->dg.p, bad.p));
+                                                                                c->bcflag.p, e->ks.p, e->dg.p, e->drow.p,
+                                                                                (size_t)e->nchunks * e->R, bad.p));
   ENS_DISPATCH(e->LB, k_ens_bcast<LB><<<(unsigned)blocks, HF_ET, 0, c->stream>>>(N, c->u.p, e->u.p));
   ENS_DISPATCH(e->LB, k_ens_bcast<LB><<<(unsigned)blocks, HF_ET, 0, c->stream>>>(N, c->gfull.p, e->g.p));
   HF_CUDA(cudaGetLastError());
@@ -838,7 +855,7 @@ static int ens_set_smem(EnsState* e) {
 static void ens_launch_iteration(hf_ctx* c, EnsState* e, int par) {
   const EnsPatch P{e->nchunks,    e->mcap,         e->halo_cap, e->nstages, (unsigned)e->stage_bytes, e->halo_ptr.p,
                    e->halo_idx.p, e->rowptr_pad.p, e->lc_off.p, e->lcol.p,  e->bs.p};
-  ENS_DISPATCH(e->LB, k_ens_iter<LB><<<e->igrid, HF_ENT, e->iter_smem, c->stream>>>(P, par, e->ks.p, e->dg.p, e->x.p, e->z.p, e->z1.p,
+  ENS_DISPATCH(e->LB, k_ens_iter<LB><<<e->igrid, HF_ENT, e->iter_smem, c->stream>>>(P, par, e->ks.p, e->drow.p, (size_t)e->nchunks * e->R, e->x.p, e->z.p, e->z1.p,
                                                                                    e->p0.p, e->p1.p, e->w.p, e->w1.p, e->part.p,
                                                                                    e->ctrl.p));
 }
@@ -1036,6 +1053,20 @@ run_again:
       // an on-chip solve hit the iteration cap or left the fixed-point range of its reduction: the state it left is
       // not trustworthy, the whole run is repeated from its initial state with the streaming kernels (still the GPU)
       c->stat_retries += 1;
+      if (getenv("HF_DEBUG")) {
+        HF_CUDA(cudaMemcpyAsync(e->h_ctrl, e->ctrl.p, sizeof(EnsCtrl), cudaMemcpyDeviceToHost, c->stream));
+        HF_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<int> hit(n_steps);
+        e->oc_iters.download(hit.data(), n_steps, c->stream);
+        fprintf(stderr, "[hf debug] on-chip ensemble run failed: fail=%d last it=%d done=%d rz=%g %g %g %g thr=%g active=%d%d%d%d iters:",
+                nfail, e->h_ctrl->it, e->h_ctrl->done, e->h_ctrl->rz[0], e->h_ctrl->rz[1], e->h_ctrl->rz[2], e->h_ctrl->rz[3],
+                e->h_ctrl->thr[0], e->h_ctrl->active[0], e->h_ctrl->active[1], e->h_ctrl->active[2], e->h_ctrl->active[3]);
+        for (int s = 0; s < n_steps; ++s) fprintf(stderr, " %d", hit[s]);
+        fprintf(stderr, "\n");
+      }
+      // the failed run may have left non-finite values behind, also in the padding rows that the recycle kernels sum over
+      for (DevBuf<double>* v : {&e->x, &e->z, &e->z1, &e->p0, &e->p1, &e->w, &e->w1, &e->rc_d, &e->rc_ad})
+        if (v->n) HF_CUDA(cudaMemsetAsync(v->p, 0, v->n * sizeof(double), c->stream));
       HF_CUDA(cudaMemcpyAsync(e->u.p, e->oc_u0.p, sizeof(double) * nbp, cudaMemcpyDeviceToDevice, c->stream));
       HF_CUDA(cudaMemcpyAsync(e->uprev.p, e->oc_u0.p + nbp, sizeof(double) * nbp, cudaMemcpyDeviceToDevice, c->stream));
       e->have_prev = had_prev;

@@ -10,10 +10,21 @@
 //     base0 + k_b S0 (hf_ensemble.cu) - S0 entries only exist in the slices that touch sample cells, and when all
 //     variants of the tile share k (a sweep sorted by k: 64 heating widths per conductivity) they are folded
 //     into the values on the host side of the launch;
-//   * the latency of the grid reduction (~1.5 us from the arrival of the partial sums to the result) is paid once for
-//     B/NH variants, and with NH = 2 the tile is advanced as two half-tiles in lock step - while the reduction of one
-//     half is in flight through L2, the CTA computes the SpMV of the other half (software pipelining across
-//     variants instead of across iterations: classic CG recurrences, no extra vectors).
+//   * the latency of the grid reduction (~1.5 us from the arrival of the partial sums to the result) is paid once per
+//     iteration of the whole tile.  NH = 2 (HF_ENS_NH) advances the tile as two half-tiles in lock step, the
+//     reduction of one half in flight while the CTA computes the SpMV of the other (software pipelining across
+//     variants instead of across iterations: classic CG recurrences, no extra vectors) - measured slower (10.2 us per
+//     iteration of the tile against 7.2 us) because the per-half passes repeat the operator decode and the halo fetch
+//     of a half only starts after the other half's SpMV; kept as a tested option, NH = 1 is the default.
+// Measured (B200, N = 141 783, 139 CTAs, tile of 4 with one conductivity, clock64 per phase, cycles per iteration of
+// the tile): SpMV + dot products 6300, arrive 1800, reduction trip 3300 (halo fetch 1750 hidden in it), updates 2200:
+// 7.2 us = 1.8 us per variant and iteration against 2.4 - 2.7 us for the single-simulation kernel.  What bounds it is
+// shared-memory bandwidth, not latency: every row moves ~560 B per iteration for the four variants (272 B of
+// gathers, the rest own-row p / z / w / 1/d reads and writes) = 4500 cycles at 128 B/clk, and random 16-byte
+// gathers reach 54 B/clk (tools/ubench_fp64.cu) - batching shares the operator and the reduction but not the
+// vector traffic, so 4 variants cost ~2.7 x one.  End to end a tile of 4 takes 31.8 ms per simulation (100 steps,
+// recycled bases) against 40 ms alone and 34 ms with two simulations sharing the SMs (sweep 'serial' engine), which
+// therefore stays the default of parameter_sweep on on-chip meshes; `--mode ensemble --batch 4` selects this kernel.
 // Formulation as in hf_ensemble.cu: z = D^-1 r, p, w = D^-1 A p, so halo rows need no per-variant scaling:
 //     t = A_b p ; w = t / d ;  (p,t), (z,t), (t,w)  -> one reduction ;  alpha = rz / (p,t)
 //     x += alpha p ; z -= alpha w ; rz' = rz - 2 alpha (z,t) + alpha^2 (t,w) ; p = z + (rz'/rz) p
@@ -34,7 +45,7 @@
 #define EP_W (EP_T / 32)
 
 struct EnsOcArgs {
-  int nslices, max_it, mat_cap, s0_cap, halo_cap, eb_shift;
+  int nslices, nrows, max_it, mat_cap, s0_cap, halo_cap, eb_shift;   // nrows: rows of the mesh (rows beyond it are padding)
   const int* slice_ptr;
   const double* val;             // sliced-ELL values: base0 (+ k S0 for uniform tiles)
   const double* s0;              // sliced-ELL values of S0
@@ -53,6 +64,8 @@ struct EnsOcArgs {
   unsigned long long* acc;
   int* iters_out;
   int* fail;
+  unsigned* gen;                 // [2] packet / reduction generation per half-tile, monotonic across launches: the packet
+                                 // buffers still hold the previous solve's packets, whose tags must never match again
   long long* phase;              // diagnostics (-DHF_PHASE_TIMING): [G][2][8] clock64 cycles per phase, warps 0 and 1
 };
 
@@ -336,7 +349,7 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
   bool done[NH];
 #pragma unroll
   for (int g = 0; g < NH; ++g) {
-    gen[g] = 0u;
+    gen[g] = P.gen[g];
     it[g] = 0;
     done[g] = s_ctl[g * 4 + 1] != 0;
   }
@@ -637,7 +650,7 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
   EP_PT_STORE
 #pragma unroll
   for (int k = 0; k < EP_RPT; ++k)
-    if (wid[k] >= 0) {
+    if (wid[k] >= 0 && lo + (warp * EP_RPT + k) * 32 + lane < P.nrows) {      // padding rows keep their zeros
       const size_t gi = ((size_t)lo + (warp * EP_RPT + k) * 32 + lane) * B;
 #pragma unroll
       for (int q = 0; q < 2; ++q) *reinterpret_cast<double2*>(P.x + gi + 2 * q) = make_double2(x[k][2 * q], x[k][2 * q + 1]);
@@ -652,6 +665,8 @@ __global__ void __launch_bounds__(EP_T, 1) k_ens_patch(EnsOcArgs P) {
       P.c->active[b] = s_act[b];
       bad = bad || s_act[b] || !isfinite(s_rz[b]);
     }
+#pragma unroll
+    for (int g = 0; g < NH; ++g) P.gen[g] = gen[g];
     P.c->it = itmax;
     P.c->done = bad ? 0 : 1;
     if (P.iters_out) *P.iters_out = itmax;
@@ -810,6 +825,7 @@ int hf_ens_oc_plan(hf_ctx* c, EnsState* e) {
   HF_TRY(e->oc_acc.alloc(acc_words, c->stream));
   HF_TRY(e->oc_qpk.alloc((size_t)2 * (e->oc_rows + EP_R) * B, c->stream));
   HF_TRY(e->oc_fail.alloc(1, c->stream));
+  HF_TRY(e->oc_gen.alloc(2, c->stream));
   e->oc_ok = true;
   return HF_OK;
 }
@@ -823,6 +839,7 @@ int hf_ens_oc_solve_async(hf_ctx* c, EnsState* e, int step_slot) {
   HF_CUDA(cudaMemsetAsync(e->oc_acc.p, 0, e->oc_acc.n * sizeof(unsigned long long), c->stream));
   EnsOcArgs a;
   a.nslices = op.nslices;
+  a.nrows = c->N;
   a.max_it = c->max_iters;
   a.mat_cap = e->oc_mat_cap;
   a.s0_cap = e->oc_s0_cap;
@@ -847,6 +864,7 @@ int hf_ens_oc_solve_async(hf_ctx* c, EnsState* e, int step_slot) {
   a.acc = e->oc_acc.p;
   a.iters_out = (step_slot >= 0 && (size_t)step_slot < e->oc_iters.n) ? e->oc_iters.p + step_slot : nullptr;
   a.fail = e->oc_fail.p;
+  a.gen = e->oc_gen.p;
   a.phase = c->debug_phase.n ? c->debug_phase.p : nullptr;
   void* args[] = {&a};
   HF_CUDA(cudaFuncSetAttribute(ep_kernel(e->oc_nh), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->oc_smem));

@@ -279,9 +279,14 @@ def _rank_share(base_config, combinations, mesh_folder, batch, device, tiles, su
             warm[0].join()
 
 
+def _mesh_marker(mesh_folder):
+    """Marker file next to (not inside) the mesh folder, which keeps the reference's two files only."""
+    return os.path.normpath(mesh_folder) + ".ready"
+
+
 def _wait_for_mesh(mesh_folder, mesh_file, mesh_cfg_file, timeout_s=7200.0):
-    """Ranks > 0: block until rank 0 has marked the group's mesh files complete (``.mesh_ready``)."""
-    marker = os.path.join(mesh_folder, '.mesh_ready')
+    """Ranks > 0: block until rank 0 has marked the group's mesh files complete (``<mesh folder>.ready``)."""
+    marker = _mesh_marker(mesh_folder)
     t0 = time.time()
     while not (os.path.exists(marker) and os.path.exists(mesh_file) and os.path.exists(mesh_cfg_file)):
         if time.time() - t0 > timeout_s:
@@ -301,7 +306,9 @@ def _warm_up_collectives(local_rank):
                 return                               # spawned workers without a process group: nothing to warm up
             if dist.get_backend() == "nccl":
                 torch.cuda.set_device(local_rank)
-            dist.barrier()
+            # the same collective as the final gather (sweep.gather_results), so that its connections exist
+            bucket = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+            dist.gather_object({"warm": dist.get_rank()}, bucket, dst=0)
         except Exception:
             pass                                     # the gather itself will report a broken process group
     t = threading.Thread(target=work, daemon=True)
@@ -407,8 +414,8 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
         if rank == 0:
             os.makedirs(mesh_folder, exist_ok=True)
             if not (os.path.exists(mesh_file) and os.path.exists(mesh_cfg_file)):
-                if os.path.exists(os.path.join(mesh_folder, '.mesh_ready')):
-                    os.remove(os.path.join(mesh_folder, '.mesh_ready'))
+                if os.path.exists(_mesh_marker(mesh_folder)):
+                    os.remove(_mesh_marker(mesh_folder))
                 say(f"  Building new mesh for width {width:.2e} m")
                 config = modify_config_for_parameters(base_config, combinations[0]['fwhm'], combinations[0]['k'], width)
                 _, stack = _runner_for(config)
@@ -417,7 +424,7 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
                     prepare_mesh(config, stack, mesh_folder, rebuild_mesh=True)
             else:
                 say(f"  Reusing existing mesh for width {width:.2e} m")
-            with open(os.path.join(mesh_folder, '.mesh_ready'), 'w') as f:      # both files are complete
+            with open(_mesh_marker(mesh_folder), 'w') as f:      # both files are complete
                 f.write("ok\n")
         elif world > 1:
             # the other ranks wait for rank 0's mesh files through the file system - no collective, so the NCCL
@@ -471,8 +478,12 @@ def run_parameter_sweep(base_config_path, output_dir, fwhm_range, k_range, width
 
     if mode != "per_run":
         cat = lambda parts, dt: np.concatenate(parts) if parts else np.zeros(0, dt)
+        if os.environ.get("HF_SWEEP_TIMING"):
+            print(f"[sweep timing] rank {rank}: at the final gather after {time.time() - t_sweep:.2f}s", file=sys.stderr, flush=True)
         gathered = sweep.gather_results(offset, 0, 0, cat(my_idx, np.int64), None, cat(my_iters, np.int64),
                                         cat(my_secs, np.float64), my_errors)       # the single collective of the sweep
+        if os.environ.get("HF_SWEEP_TIMING"):
+            print(f"[sweep timing] rank {rank}: gathered after {time.time() - t_sweep:.2f}s", file=sys.stderr, flush=True)
         if rank == 0:
             _, iters, secs, errors = gathered
             for off, combinations in group_offset:

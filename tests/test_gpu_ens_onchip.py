@@ -76,12 +76,13 @@ def test_on_chip_tile_with_runner_defaults_is_reproducible_and_agrees_with_strea
     assert it1.sum() < 0.6 * it0.sum()
 
 
-def test_failed_on_chip_tile_is_repeated_with_the_streaming_kernels(wd):
+@pytest.mark.parametrize("recycle,warm", [(0, 0.0), (64, 1.0)])
+def test_failed_on_chip_tile_is_repeated_with_the_streaming_kernels(wd, recycle, warm):
     c = wd
     S = 12
     ks, fw = [5.0, 5.0, 5.0, 5.0], [1e-6, 4e-6, 2e-5, 1e-4]
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 3e-8, 0.0)])
-    s = make_solver(c, ordering="hilbert")
+    s = make_solver(c, ordering="hilbert", recycle=recycle, warm=warm)
     s.ens_create(ks, [problem.gaussian_coeff(f) for f in fw], sample_tag(c))
     assert s.ens_path() == 5
     _lib.check(s._L.hf_debug_fx_shift(s._h, 60))                    # partial sums leave the fixed-point range
@@ -91,7 +92,7 @@ def test_failed_on_chip_tile_is_repeated_with_the_streaming_kernels(wd):
     s.ens_destroy()
     s.close()
     # same steps on a clean context (on-chip, no failure): the repeated run gives the same temperatures
-    _, h_ok, _, _, st = run_tile(c, ks, fw, S, watch, first=10)
+    _, h_ok, _, _, st = run_tile(c, ks, fw, S, watch, first=10, recycle=recycle, warm=warm)
     assert st["retries"] == 0
     assert np.abs(hist / h_ok - 1).max() <= 2e-11
 
