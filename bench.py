@@ -21,6 +21,7 @@ Extra objects on the JSON line:
                 refinement of ``cfgs/konopkova.yaml`` (BASELINE config #4), timed inside real solves;
                 ``roofline_1m_launch_per_iteration``: the same with ``k_pcg_iter`` (round-1 scheme).
   roofline_4m   the same on a 4.3 M-dof refinement: 580 MB per iteration, far beyond the L2.
+  roofline_ens_1m  ``k_ens_iter`` (batched multi-RHS ensemble, 16 sweep variants per tile) on the same >= 1 M-dof mesh.
   sweep         BASELINE config #5 through ``run_parameter_sweep``: 128 variants per GPU, run folders written;
                 ``config.sweep_sims_per_s`` / ``config.sweep_cpu_sims_per_s`` repeat the two numbers.
   cpu_baseline  the scipy sparse-LU oracle on this host (1 core), same steps; ``parity_check`` compares the GPU
@@ -280,6 +281,40 @@ def streaming_roofline(case, device, rtol, peak, peak_src, steps, traffic=None, 
                    "with the L2 flushed in between"}
 
 
+def ensemble_roofline(case, device, rtol, peak, peak_src, B=16, steps=2, traffic=None):
+    """north_star (c) on a mesh that streams from HBM: `k_ens_iter` advancing B sweep variants at once (one launch per PCG
+    iteration of the whole tile), timed inside real solves.  Algorithmic bytes per launch: per dof
+    and variant x z w p read + written (64 B), per row the diagonal pair (16 B), per non-zero two fp64 value arrays
+    and a 16-bit local column (18 B) + 4 B row pointer, shared by the B variants."""
+    from heatflow_b200 import problem
+    s = configured_solver(case, device, rtol, warm=0.0, ordering="hilbert")
+    n, nnz = s.sizes()
+    s.set_state(np.full(n, case.ic))
+    tag = int(case.tags[[m.name for m in case.mats].index("p_sample")])
+    ks = np.logspace(0, 2, 64)[20:20 + B]
+    cf = [problem.gaussian_coeff(f) for f in np.logspace(-6, -4, 64)[10:10 + B]]
+    s.ens_create(ks, cf, tag)
+    k0 = min(10, max(0, case.num_steps - steps - 1))
+    s.ens_run(case.amps[k0:k0 + 1], case.ic, [0])                       # warm-up: graphs captured
+    s.set_profile(True)
+    _, iters = s.ens_run(case.amps[k0 + 1:k0 + 1 + steps], case.ic, [0])
+    solve_ms, _ = s.solve_profile()
+    s.set_profile(False)
+    path = s.ens_path()
+    s.ens_destroy()
+    s.close()
+    its = max(1, int(iters.sum()))
+    us = solve_ms * 1e3 / its
+    alg = n * (64.0 * B + 16.0) + 18.0 * nnz + 4.0 * n
+    ach = alg / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "k_ens_iter" if path == 1 else "k_ens_patch", "variants": B, "achieved": ach, "peak": peak,
+            "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg, "launch_us": us,
+            "pcg_iterations": its, "n_dofs": n, "nnz": nnz, "us_per_iteration_and_variant": us / B,
+            "dof_iterations_per_s": n * B / (us * 1e-6), "peak_source": peak_src,
+            "how": f"CUDA events around the PCG solves of {steps} time steps of a {B}-variant tile / PCG iterations of the tile "
+                   "(host polls between graph chunks and launches queued past convergence count against it)"}
+
+
 def large_mesh_run(case, device, rtol, warm, recycle):
     """BASELINE config #4: the whole konopkova run on the >= 1 M-dof mesh with the runner defaults."""
     s = configured_solver(case, device, rtol, warm=warm, recycle=recycle)
@@ -507,6 +542,7 @@ def run_ours(args, rank, world, local_rank):
                                                  traffic=traffic.get("k_pcg_stream_1m"))
         line["roofline_1m_launch_per_iteration"] = streaming_roofline(cl, local_rank, args.rtol, peak, peak_src, steps=2,
                                                                      traffic=traffic.get("k_pcg_iter_1m"), mode=1)
+        line["roofline_ens_1m"] = ensemble_roofline(cl, local_rank, args.rtol, peak, peak_src, traffic=traffic.get("k_ens_iter_b16_1m"))
         line["konopkova_1m"] = large_mesh_run(cl, local_rank, args.rtol, args.warm_start, min(args.recycle, 64))
         # DRAM-honest: 4.3 M dofs, 580 MB per PCG iteration - nothing survives in the 126 MB L2 between iterations
         # (bandwidth measurement only: the fast 'rows' mesher - Delaunay of 4.3 M points would take minutes)

@@ -199,17 +199,17 @@ def _group_on_device(base_config, combinations, mesh_folder, batch, device, tile
     _, stack = _runner_for(cfg0)
     t_setup = time.time()
     timing = bool(os.environ.get("HF_SWEEP_TIMING"))
+    # serial engine on an on-chip mesh: two simulations share the SMs (hf_set_sharing) when the mesh still fits with
+    # half the registers / shared memory per CTA - planned for that from the start (re-planning costs 0.3 s)
+    n_mine = sum(len(t) for t in tiles)
+    want_pair = engine in ("auto", "serial") and (n_mine > 1 or share is not None)
     with suppress_output(suppress_print):
-        sim = Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device)
+        sim = Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device, sharing=2 if want_pair else 1)
     extra = []
     writer = None
     try:
-        # serial engine on an on-chip mesh: two simulations share the SMs (hf_set_sharing) when the mesh
-        # still fits with half the registers / shared memory per CTA
-        n_mine = sum(len(t) for t in tiles)
-        if engine in ("auto", "serial") and n_mine > 1 and sim.solver.on_chip():
+        if want_pair:
             with suppress_output(suppress_print):
-                sim.set_sharing(2)
                 if sim.solver.on_chip():
                     extra.append(Simulation2D(cfg0, stack, mesh_folder, rebuild_mesh=False, device=device, sharing=2))
                 else:
