@@ -624,7 +624,7 @@ static const int kPatchRpt[6] = {4, 6, 8, 10, 12, 14};
 static const int kPatchK[2][6] = {{8, 6, 4, 4, 3, 2}, {2, 1, 0, 0, 0, 0}};   // [share - 1][rows-per-thread index]
 // the pipelined variant keeps six vectors of the own rows in registers, so it caches fewer operator entries (-1: no such
 // kernel); the shared-memory operator part is sized for the smaller of the two caches
-static const int kPipeK[2][6] = {{8, -1, -1, -1, -1, -1}, {1, -1, -1, -1, -1, -1}};
+static const int kPipeK[2][6] = {{8, -1, -1, -1, -1, -1}, {-1, -1, -1, -1, -1, -1}};
 
 static const void* patch_kernel(int rpt, int share) {
   if (share == 2) {
@@ -648,12 +648,10 @@ static const void* patch_kernel(int rpt, int share) {
 }
 // pipelined variant: x r p s z w of the own rows live in registers, so it exists for the small rows-per-thread counts
 static const void* pipe_kernel(int rpt, int share) {
-  if (share == 2) {
-    switch (rpt) {
-      case 4: return (const void*)k_pcg_pipe<4, 1, 2>;
-      default: return nullptr;
-    }
-  }
+  // two co-resident solves (hf_set_sharing(2)) already hide each other's reduction trip, and with half the register
+  // file the six own-row vectors of the pipelined kernel leave room for one cached operator entry only: measured
+  // 28.7 simulations/s with k_pcg_pipe<4, 1, 2> against 32.4 with the classic k_pcg_patch<4, 2, 2> (two host threads)
+  if (share == 2) return nullptr;
   switch (rpt) {
     case 4: return (const void*)k_pcg_pipe<4, 8, 1>;       // rpt 6 (K = 4) measured 2 % slower than the classic kernel
     default: return nullptr;
