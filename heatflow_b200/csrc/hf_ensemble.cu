@@ -236,7 +236,7 @@ struct EnsPatch {
 };
 
 // Stage layout (bytes, every block a multiple of 16):
-//   bs[mcap] double2 | x[EP] | z[EP] | w[EP] | d[EP] | p[EP] | halo p[halo_cap*B] | lcol[mcap] u16 | rowptr[R+4] i32
+//   bs[mcap] double2 | x[EP] | z[EP] | w[EP] | (base0_ii, S0_ii)[2][R] | p[EP] | halo p[halo_cap*B] | lcol[mcap] u16 | rowptr[R+4] i32
 template <int LB>
 __device__ __forceinline__ void ens_issue_chunk(const EnsPatch& P, int ch, int k0, int k1, int lc0, unsigned char* st,
                                                 const double* x, const double* zo, const double* wo, const double* drow,
@@ -245,7 +245,7 @@ __device__ __forceinline__ void ens_issue_chunk(const EnsPatch& P, int ch, int k
   constexpr int R = HF_EPAIRS / B;
   constexpr unsigned vb = HF_EPAIRS * 8u;
   unsigned char* sx = st + (size_t)P.mcap * 16;
-  unsigned char* slc = sx + 5 * (size_t)vb + (size_t)P.halo_cap * B * 8;
+  unsigned char* slc = sx + 4 * (size_t)vb + 2 * (size_t)R * 8 + (size_t)P.halo_cap * B * 8;
   unsigned char* srow = slc + (size_t)P.mcap * 2;
   const unsigned n = (unsigned)(k1 - k0);
   const unsigned ncol = (n + 7u) & ~7u;
@@ -261,7 +261,7 @@ __device__ __forceinline__ void ens_issue_chunk(const EnsPatch& P, int ch, int k
   ens_bulk(sx + 2 * vb, wo + lo, vb, bar, keep);
   ens_bulk(sx + 3 * vb, drow + (size_t)ch * R, R * 8u, bar, keep);              // base0_ii of the chunk's rows
   ens_bulk(sx + 3 * vb + R * 8u, drow + rows + (size_t)ch * R, R * 8u, bar, keep);   // S0_ii
-  ens_bulk(sx + 4 * vb, po + lo, vb, bar, keep);
+  ens_bulk(sx + 3 * vb + 2 * R * 8u, po + lo, vb, bar, keep);
   ens_bulk(srow, P.rowptr_pad + (size_t)ch * R, (R + 4) * 4u, bar, keep);
   if (ncol) ens_bulk(slc, P.lcol + lc0, ncol * 2u, bar, keep);
   for (unsigned off = 0; off < n * 16u; off += 16384u)
@@ -369,7 +369,7 @@ k_ens_iter(EnsPatch P, int par, const double* __restrict__ ks, const double* __r
     double* sz = sx + HF_EPAIRS;
     double* sw = sz + HF_EPAIRS;
     double* sd = sw + HF_EPAIRS;
-    double* sp = sd + HF_EPAIRS;        // own pairs, halo pairs follow at sp[HF_EPAIRS + ...]
+    double* sp = sd + 2 * R;            // own pairs, halo pairs follow at sp[HF_EPAIRS + ...]
     const unsigned short* slc = reinterpret_cast<const unsigned short*>(sp + HF_EPAIRS + (size_t)P.halo_cap * B);
     const int* srow = reinterpret_cast<const int*>(slc + P.mcap);
     const size_t g0 = (size_t)ch * HF_EPAIRS;
@@ -809,7 +809,7 @@ extern "C" int hf_ens_create(hf_ctx* c, int32_t batch, const double* k_sample, c
     k_ens_pack<<<(unsigned)((c->nnz + 255) / 256), 256, 0, c->stream>>>(c->nnz, e->base0.p, e->s0.p, e->bs.p);
     HF_CUDA(cudaGetLastError());
     e->halo_cap = (e->halo_max + 1) & ~1;
-    e->stage_bytes = ((size_t)e->mcap * 18 + sizeof(double) * ((size_t)5 * HF_EPAIRS + (size_t)e->halo_cap * B) + 4 * (e->R + 4) + 127) &
+    e->stage_bytes = ((size_t)e->mcap * 18 + sizeof(double) * ((size_t)4 * HF_EPAIRS + 2 * (size_t)e->R + (size_t)e->halo_cap * B) + 4 * (e->R + 4) + 127) &
                      ~(size_t)127;
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
