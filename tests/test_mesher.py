@@ -220,3 +220,31 @@ def test_material_validation():
     with pytest.raises(RuntimeError):
         with contextlib.redirect_stdout(io.StringIO()):
             dup.build_mesh()
+
+
+def test_msh_side_cache_is_used_and_invalidated(tmp_path):
+    # Mesh.msh_to_dolfinx keeps the parsed arrays in a binary side file next to the mesh folder (the folder itself keeps
+    # the reference's two files); a rewritten mesh.msh (other size / mtime) must not be served from the old cache
+    import os
+    import time
+    from heatflow_b200.mesh_and_materials.mesh import Mesh
+    from heatflow_b200.mesh_and_materials.msh_io import write_msh
+    folder = tmp_path / "meshes" / "w1"
+    folder.mkdir(parents=True)
+    path = str(folder / "mesh.msh")
+    nodes = np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0]])
+    tris = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.int32)
+    write_msh(path, nodes, tris, np.array([1, 2]), {1: "a", 2: "b"})
+    d1, t1, _ = Mesh.msh_to_dolfinx(path)
+    side = str(tmp_path / "meshes" / "w1") + ".msh_cache.npz"
+    assert os.path.isfile(side) and sorted(os.listdir(folder)) == ["mesh.msh"]
+    Mesh._msh_cache.clear()                                      # force the side file to be read
+    d2, t2, _ = Mesh.msh_to_dolfinx(path)
+    assert np.array_equal(d1.geometry.x, d2.geometry.x) and np.array_equal(d1.cells, d2.cells)
+    assert np.array_equal(t1.values, t2.values)
+    time.sleep(0.01)
+    nodes2 = np.vstack([nodes, [[2.0, 0.5]]])
+    tris2 = np.vstack([tris, [[1, 4, 2]]]).astype(np.int32)
+    write_msh(path, nodes2, tris2, np.array([1, 2, 2]), {1: "a", 2: "b"})
+    d3, t3, _ = Mesh.msh_to_dolfinx(path)
+    assert d3.geometry.x.shape[0] == 5 and len(t3.values) == 3

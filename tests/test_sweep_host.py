@@ -197,3 +197,27 @@ def test_serial_engine_share_is_a_partition_with_every_conductivity_on_every_ran
     assert max(means) - min(means) < 0.2                       # tiles of 16: the difference is ln(10) = 2.3
     for s in shares:
         assert len(np.unique(k[s])) == 32
+
+
+def test_mesh_hand_over_marker_and_wait(tmp_path):
+    # ranks > 0 wait for rank 0's mesh through the file system: marker next to the folder, both files required
+    import threading
+    import time
+    from heatflow_b200 import parameter_sweep as psw
+    folder = tmp_path / "meshes" / "width_1"
+    folder.mkdir(parents=True)
+    mesh, cfg = str(folder / "mesh.msh"), str(folder / "mesh_cfg.yaml")
+    assert psw._mesh_marker(str(folder)) == str(folder) + ".ready"
+    with pytest.raises(TimeoutError):
+        psw._wait_for_mesh(str(folder), mesh, cfg, timeout_s=0.1)
+    def rank0():
+        time.sleep(0.1)
+        open(cfg, "w").write("a: 1\n")
+        open(mesh, "w").write("$MeshFormat\n")
+        open(psw._mesh_marker(str(folder)), "w").write("ok\n")
+    t = threading.Thread(target=rank0)
+    t.start()
+    t0 = time.time()
+    psw._wait_for_mesh(str(folder), mesh, cfg, timeout_s=10.0)
+    t.join()
+    assert 0.05 < time.time() - t0 < 5.0 and sorted(os.listdir(folder)) == ["mesh.msh", "mesh_cfg.yaml"]
