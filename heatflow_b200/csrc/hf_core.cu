@@ -192,6 +192,37 @@ extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const do
       c->h_order[n] = keyed[n].second;
       c->h_rank[keyed[n].second] = n;
     }
+    // Meshes of at most one 1024-row patch per SM run in the on-chip kernels with four 32-row slices per warp
+    // (hf_patch.cu, rpt = 4).  There the rows whose q value a neighbouring patch needs ("boundary" rows: a cell joins
+    // them to a node of another patch, ~250 of 1024) are moved into the FIRST slice of every warp, the interior rows
+    // into the other three: a warp publishes its boundary packets after a quarter of its SpMV and computes the interior
+    // rows while they travel through L2, instead of publishing at the end and waiting a full trip for the neighbours'.
+    // The patches themselves (sets of rows, halo lists) do not change; inside a class the Hilbert order is kept.
+    if (nv == 3 && !getenv("HF_NO_BOUNDARY_FIRST") && ((int64_t)N + 1023) / 1024 <= c->sm_count) {
+      constexpr int PB = 1024, SPW = 4;                       // rows per patch, slices per warp
+      std::vector<unsigned char> bnd(N, 0);
+      for (int e = 0; e < E; ++e) {
+        const int a = c->h_rank[cells_user[3 * e]] / PB, b = c->h_rank[cells_user[3 * e + 1]] / PB,
+                  d = c->h_rank[cells_user[3 * e + 2]] / PB;
+        if (a != b || a != d)
+          for (int v = 0; v < 3; ++v) bnd[cells_user[3 * e + v]] = 1;   // conservative: every node of a straddling cell
+      }
+      std::vector<int> fresh(N);
+      for (int lo = 0; lo < N; lo += PB) {
+        const int cnt = std::min(PB, N - lo), nsl = (cnt + 31) / 32;
+        std::vector<int> slots;                                // positions of the block in filling order: slice class 0, 1, 2, 3
+        slots.reserve(cnt);
+        for (int cls = 0; cls < SPW; ++cls)
+          for (int sl = cls; sl < nsl; sl += SPW)
+            for (int l = 0; l < 32 && sl * 32 + l < cnt; ++l) slots.push_back(lo + sl * 32 + l);
+        int at = 0;
+        for (int pass = 1; pass >= 0; --pass)                  // boundary rows first, then interior rows, each in Hilbert order
+          for (int pos = lo; pos < lo + cnt; ++pos)
+            if ((int)bnd[c->h_order[pos]] == pass) fresh[slots[at++]] = c->h_order[pos];
+      }
+      c->h_order.swap(fresh);
+      for (int n = 0; n < N; ++n) c->h_rank[c->h_order[n]] = n;
+    }
     xy_store.resize((size_t)N * 2);
     for (int n = 0; n < N; ++n) {
       xy_store[2 * n] = xy_user[2 * c->h_order[n]];

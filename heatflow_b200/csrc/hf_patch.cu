@@ -434,7 +434,11 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_pipe(PatchArgs P) {
   unsigned gen = *P.gen;
   __syncthreads();
   // one SpMV from shared memory: out[k] = sum_j Ahat_kj v_j with v on own + halo rows in sw
-  auto spmv = [&](double (&out)[RPT]) {
+  // pub_buf >= 0: the result of a boundary row is published (packet buffer pub_buf, tag pub_tag) as soon as it is
+  // computed - hf_set_mesh puts the boundary rows into the first slice of every warp, so the packets leave after a
+  // quarter of the SpMV
+  auto spmv = [&](double (&out)[RPT], const int pub_buf, const unsigned pub_tag) {
+    uint4* qpub = P.qpk + (size_t)(pub_buf < 0 ? 0 : pub_buf) * P.npad;
 #pragma unroll
     for (int k = 0; k < RPT; ++k) {
       out[k] = 0.0;
@@ -455,15 +459,13 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_pipe(PatchArgs P) {
         }
         if (kk < wd) a0 = fma(sval[b + kk * 32], sw[scol[b + kk * 32]], a0);
         out[k] = a0 + a1;
+        if (pub_buf >= 0 && (pubmask & (1u << k))) hf_pkt_store_nb(qpub + lo + (warp * RPT + k) * 32 + lane, out[k], pub_tag);
       }
     }
   };
-  // publish the boundary rows of v as packets tagged `tag` in buffer `buf`, fetch the halo rows into dst[0 .. nh)
-  auto exchange = [&](const double (&v)[RPT], int buf, unsigned tag, double* dst, bool skip_warp0) {
+  // fetch the halo rows of the vector the neighbours published as packets tagged `tag` in buffer `buf` into dst[0 .. nh)
+  auto exchange = [&](int buf, unsigned tag, double* dst, bool skip_warp0) {
     uint4* qout = P.qpk + (size_t)buf * P.npad;
-#pragma unroll
-    for (int k = 0; k < RPT; ++k)
-      if (wid[k] >= 0 && (pubmask & (1u << k))) hf_pkt_store(qout + lo + (warp * RPT + k) * 32 + lane, v[k], tag);
     if (skip_warp0 && warp == 0) return;
     const int first = skip_warp0 ? 32 : 0;
     const int NP = HF_PT - first;
@@ -508,8 +510,8 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_pipe(PatchArgs P) {
   hf_fx_load_state(fx, P.acc_prev);
   if (!done && P.max_it > 0) {
     // ---- w_0 = Ahat r_0 on the own rows, then on the halo rows (packets in buffer 1, tag gen + 1)
-    spmv(w);
-    exchange(w, 1, gen + 1u, sqh, false);
+    spmv(w, 1, gen + 1u);
+    exchange(1, gen + 1u, sqh, false);
     __syncthreads();                               // every thread has read r_0 from sw
 #pragma unroll
     for (int k = 0; k < RPT; ++k)
@@ -530,16 +532,16 @@ __global__ void __launch_bounds__(HF_PT, MINB) k_pcg_pipe(PatchArgs P) {
     }
     const int e_g = hf_exp2(gam_est);
     const int eb2[2] = {hf_clamp_exp(e_g + HF_FX_MARGIN - P.eb_shift), hf_clamp_exp(e_g + 4 + HF_FX_MARGIN)};
-    hf_fx_arrive<2>(d, eb2, P.acc, gen, red, P.fail);
+    hf_fx_arrive_warp<2>(d, eb2, P.acc, gen, P.fail);
     HF_PT_MARK(0);
     // ---- q = Ahat w while the reduction is in flight; halo q packets
     double q[RPT];
-    spmv(q);
+    spmv(q, it & 1, gen);
     HF_PT_MARK(1);
-    exchange(q, it & 1, gen, sqh, true);
+    exchange(it & 1, gen, sqh, true);
     HF_PT_MARK(2);
     double tot[2];
-    hf_fx_wait<2, 0>(tot, eb2, P.acc, G, gen, red, fx, P.fail);   // no poll delay: the SpMV has already covered the trip
+    hf_fx_wait<2, 0, HF_PW>(tot, eb2, P.acc, G, gen, red, fx, P.fail);   // no poll delay: the SpMV has already covered the trip
     HF_PT_MARK(3);
     const double gam = tot[0], delta = tot[1];
     rr = gam;

@@ -22,6 +22,12 @@ __device__ __forceinline__ void hf_pkt_store(uint4* p, double v, unsigned gen) {
   const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
   asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(gen), "r"(hi), "r"(gen) : "memory");
 }
+// the same store without the compiler-level memory barrier: for use inside the SpMV loop, where the shared-memory loads
+// of the next row slice should not wait behind it (the packet carries its own tag, nothing else is ordered against it)
+__device__ __forceinline__ void hf_pkt_store_nb(uint4* p, double v, unsigned gen) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(gen), "r"(hi), "r"(gen));
+}
 __device__ __forceinline__ uint4 hf_pkt_load(const uint4* p) {
   uint4 v;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -155,8 +161,44 @@ __device__ __forceinline__ void hf_fx_arrive(const double (&v)[NV], const int (&
   }
 }
 
-// Warp 0 polls: lane l reads the 16-byte chunk (value l & 3, replica l >> 2).
-template <int NV, int DELAY = HF_POLL_DELAY>
+// Per-warp arrival: every warp adds its own partial sums (lane i converts and adds value i) - HF_PW arrivals per CTA
+// and word instead of one, but no shared-memory stage and no barrier between the dot products and the atomics, so the
+// trip through L2 starts ~500 cycles earlier.  Readers use hf_fx_wait<NV, DELAY, HF_PW>.
+template <int NV>
+__device__ __forceinline__ void hf_fx_arrive_warp(const double (&v)[NV], const int (&eb)[NV], unsigned long long* acc, unsigned gen,
+                                                  int* fail) {
+  const int lane = threadIdx.x & 31;
+  double t = 0.0;
+  int e = eb[0];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double ti = hf_warp_sum(v[i]);
+    if (lane == i) {
+      t = ti;
+      e = eb[i];
+    }
+  }
+  if (lane < NV) {
+    const double x = hf_scale2(t, 48 - e);
+    long long hi;
+    unsigned long long lo;
+    if (fabs(x) < 281474976710656.0) {
+      const double f = floor(x);
+      hi = (long long)f;
+      lo = (unsigned long long)((x - f) * 281474976710656.0);
+    } else {
+      hi = 1ll << 54;
+      lo = 0ull;
+      atomicAdd(fail, 1);
+    }
+    unsigned long long* line = acc + ((size_t)(gen & 1u) * HF_NREP + (blockIdx.x % HF_NREP)) * HF_ACC_LINE + 2 * lane;
+    hf_red_add(line, ((unsigned long long)hi << 8) + 1ull);
+    hf_red_add(line + 1, (lo << 8) + 1ull);
+  }
+}
+
+// Warp 0 polls: lane l reads the 16-byte chunk (value l & 3, replica l >> 2).  APC = arrivals per CTA and word.
+template <int NV, int DELAY = HF_POLL_DELAY, int APC = 1>
 __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV], const unsigned long long* acc, int G, unsigned gen,
                                            double* red, FxState& st, int* fail) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -170,7 +212,8 @@ __device__ __forceinline__ void hf_fx_wait(double (&out)[NV], const int (&eb)[NV
 #pragma unroll
     for (int j = 0; j < HF_RPL; ++j) {
       const int r = (lane >> 2) + 8 * j;
-      mem[j] = (r < G && r < HF_NREP) ? (unsigned long long)((G - 1 - r) / HF_NREP + 1) : 0ull;
+      mem[j] = (r < G && r < HF_NREP) ? (unsigned long long)(((G - 1 - r) / HF_NREP + 1) * APC) : 0ull;
+      static_assert(((HF_MAX_GRID - 1) / HF_NREP + 1) * APC < 256, "the arrival count of a word lives in its low byte");
       okj[j] = !(i < NV && mem[j] > 0ull);              // inactive lanes / replicas are complete by definition
       chunk[j] = acc + ((size_t)set * HF_NREP + r) * HF_ACC_LINE + 2 * i;
       phi[j] = set ? st.hi1[j] : st.hi0[j];

@@ -6,6 +6,8 @@ import numpy as np
 from helpers import build_case
 from bench import configured_solver
 from heatflow_b200 import _lib
+if os.environ.get("HF_DEV_LIB"):
+    _lib.LIB_PATH = os.path.abspath(os.environ["HF_DEV_LIB"])
 c = build_case("geballe_with_diamond", 1.0)
 s = configured_solver(c, 0, 1e-14, warm=1.0, mode=3, recycle=0)
 n, _ = s.sizes()
