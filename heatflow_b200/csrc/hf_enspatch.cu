@@ -18,12 +18,12 @@
 //     of a half only starts after the other half's SpMV; kept as a tested option, NH = 1 is the default.
 // Measured (B200, N = 141 783, 139 CTAs, tile of 4 with one conductivity, clock64 per phase, cycles per iteration of
 // the tile): SpMV + dot products 6300, arrive 1800, reduction trip 3300 (halo fetch 1750 hidden in it), updates 2200:
-// 7.2 us = 1.8 us per variant and iteration against 2.4 - 2.7 us for the single-simulation kernel.  What bounds it is
-// shared-memory bandwidth, not latency: every row moves ~560 B per iteration for the four variants (272 B of
-// gathers, the rest own-row p / z / w / 1/d reads and writes) = 4500 cycles at 128 B/clk, and random 16-byte
+// 7.2 - 8.2 us = 1.8 - 2.1 us per variant and iteration against 2.3 us for the single-simulation pipelined kernel.  What
+// bounds it is shared-memory bandwidth, not latency: every row moves ~560 B per iteration for the four variants
+// (272 B of gathers, the rest own-row p / z / w / 1/d reads and writes) = 4500 cycles at 128 B/clk, and random 16-byte
 // gathers reach 54 B/clk (tools/ubench_fp64.cu) - batching shares the operator and the reduction but not the
-// vector traffic, so 4 variants cost ~2.7 x one.  End to end a tile of 4 takes 31.8 ms per simulation (100 steps,
-// recycled bases) against 40 ms alone and 34 ms with two simulations sharing the SMs (sweep 'serial' engine), which
+// vector traffic, so 4 variants cost ~3 x one.  End to end a tile of 4 takes 32 - 33 ms per simulation (100 steps,
+// recycled bases) against 36 ms alone and 30 - 31 ms with two simulations sharing the SMs (sweep 'serial' engine), which
 // therefore stays the default of parameter_sweep on on-chip meshes; `--mode ensemble --batch 4` selects this kernel.
 // Formulation as in hf_ensemble.cu: z = D^-1 r, p, w = D^-1 A p, so halo rows need no per-variant scaling:
 //     t = A_b p ; w = t / d ;  (p,t), (z,t), (t,w)  -> one reduction ;  alpha = rz / (p,t)
