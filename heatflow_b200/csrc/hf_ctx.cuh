@@ -162,13 +162,13 @@ struct PcgWork {
 };
 
 // Initial guess from the previous solves (hf_recycle.cu): Ahat-orthogonal corrections of up to `cap`
-// solves, kept as W, AW = Ahat W and inv[k] = 1 / (w_k . Ahat w_k); frozen once full.  The correction of the
-// last solve waits in (d, ad) with its Gram-Schmidt coefficients hn until the next projection finalises it.
+// solves, kept as W and inv[k] = 1 / (w_k . Ahat w_k); frozen once full.  The correction of the last solve waits
+// in (d, ad = Ahat d) until the next projection orthogonalises and finalises it; inc = W c of the last projection.
 struct Recycle {
   int cap = 0, count = 0, nseg = 0, nn_parts = 0;
   bool pending = false;
   size_t ld = 0;                       // row stride of W / AW (Npad rounded up to the dot-kernel segment)
-  DevBuf<double> W, AW, inv, coef, hn, parts, part_nn, d, ad, x0;
+  DevBuf<double> W, inv, coef, hn, parts, part_nn, d, ad, inc, x0;
 };
 
 struct EnsState;
