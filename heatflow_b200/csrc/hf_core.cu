@@ -858,14 +858,21 @@ k_step_init(int N, int Npad, const int* __restrict__ rowptr, const int* __restri
   }
 }
 
+// End of a time step: u_{n+1} = xhat / s, u_n -> uprev.  hf_run folds two more per-step kernels into the same launch
+// (each a 3 us launch for a few hundred threads of work): the watcher samples of this step (computed from xhat with
+// the same division, so they are the bits of u) and the Gaussian boundary values of the NEXT step.
 __global__ void k_step_finalize(int N, const double* __restrict__ xh, const double* __restrict__ scale,
-                                double* __restrict__ u, double* __restrict__ uprev) {
+                                double* __restrict__ u, double* __restrict__ uprev, int n_watch, const int* __restrict__ nodes,
+                                double* __restrict__ hist, int n_gauss, const int* __restrict__ gdof, const double* __restrict__ gr,
+                                double amp_next, double t_ic, double coeff, double* __restrict__ g) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) {
     const double un = xh[i] / scale[i];
     uprev[i] = u[i];
     u[i] = un;
   }
+  if (i < n_watch) hist[i] = xh[nodes[i]] / scale[nodes[i]];
+  if (i < n_gauss) g[gdof[i]] = (amp_next - t_ic) * exp(coeff * (gr[i] * gr[i])) + t_ic;
 }
 
 __global__ void k_sample(int n, const int* __restrict__ nodes, const double* __restrict__ u, double* __restrict__ out) {
@@ -919,14 +926,23 @@ static int finish_sync(hf_ctx* c, int* iters, double* relres) {
 }
 
 // step_slot >= 0: fully asynchronous (persistent kernel only), iteration count goes to ws.step_iters[step_slot]
+// `fuse` (hf_run): the Gaussian values of this step were written by the previous step's finalize kernel
+// (fuse->gauss_done), which also takes this step's watcher samples and the next step's Gaussian values.
+struct StepFuse {
+  bool gauss_done = false, gauss_next = false;
+  double amp_next = 0.0;
+  int n_watch = 0;
+  double* hist = nullptr;
+};
 static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double coeff, int* iters, double* relres,
-                       int step_slot, int prof_slot = -1) {
+                       int step_slot, int prof_slot = -1, const StepFuse* fuse = nullptr) {
   if (!c->op_built) return hf_fail(HF_ERR_STATE, "hf_step: operator not built");
   int path = 1;
   HF_TRY(pick_path(c, c->opA, &path));
   const bool persist = path >= 2;
-  c->stat_launches += 2 + ((use_gauss && c->n_gauss) ? 1 : 0);
-  if (use_gauss && c->n_gauss)
+  const bool gauss_now = use_gauss && c->n_gauss && !(fuse && fuse->gauss_done);
+  c->stat_launches += 2 + (gauss_now ? 1 : 0);
+  if (gauss_now)
     k_bc_gauss<<<(c->n_gauss + 255) / 256, 256, 0, c->stream>>>(c->n_gauss, c->gauss_dof.p, c->gauss_r.p, amp, t_ic, coeff,
                                                                 c->gfull.p);
   PcgWork& w = c->ws;
@@ -952,7 +968,11 @@ static int step_device(hf_ctx* c, int use_gauss, double amp, double t_ic, double
     c->stat_solve_launches += c->stat_launches - l0;
   }
   HF_TRY(hf_rc_store(c, c->opA));
-  k_step_finalize<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->N, w.x.p, c->opA.scale.p, c->u.p, c->uprev.p);
+  const int nw = fuse ? fuse->n_watch : 0, ng = (fuse && fuse->gauss_next && use_gauss) ? c->n_gauss : 0;
+  const int nthr = std::max(c->N, std::max(nw, ng));
+  k_step_finalize<<<(nthr + 255) / 256, 256, 0, c->stream>>>(c->N, w.x.p, c->opA.scale.p, c->u.p, c->uprev.p, nw, c->watch.p,
+                                                          fuse ? fuse->hist : nullptr, ng, c->gauss_dof.p, c->gauss_r.p,
+                                                          fuse ? fuse->amp_next : 0.0, t_ic, coeff, c->gfull.p);
   HF_CUDA(cudaGetLastError());
   c->have_prev = true;
   return HF_OK;
@@ -974,11 +994,14 @@ static int run_steps(hf_ctx* c, int path, int32_t n_steps, const double* amp, do
   const bool persist = path >= 2;
   for (int s = 0; s < n_steps; ++s) {
     int it = 0;
-    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr, persist ? s : -1, s));
+    StepFuse fuse;
+    fuse.gauss_done = s > 0;                         // written by the finalize kernel of step s - 1
+    fuse.gauss_next = s + 1 < n_steps;
+    fuse.amp_next = fuse.gauss_next ? amp[s + 1] : 0.0;
+    fuse.n_watch = n_watch;
+    fuse.hist = n_watch ? c->hist.p + (size_t)s * n_watch : nullptr;
+    HF_TRY(step_device(c, 1, amp[s], t_ic, coeff, &it, nullptr, persist ? s : -1, s, &fuse));
     if (iters && !persist) iters[s] = it;
-    if (n_watch) c->stat_launches += 1;
-    if (n_watch)
-      k_sample<<<(n_watch + 255) / 256, 256, 0, c->stream>>>(n_watch, c->watch.p, c->u.p, c->hist.p + (size_t)s * n_watch);
     if (fields) {
       // XDMF field output needs the state on the host after every step; the copy is stream ordered
       const double* src = c->u.p;
