@@ -39,7 +39,7 @@ DEFAULT_WARM = 1.0
 # the corrections of the last DEFAULT_RECYCLE solves (A-orthogonalised) seed the next solve by Galerkin
 # projection (hf_set_recycle): same solver, same tolerance, ~5 x fewer PCG iterations over a 100-step run
 DEFAULT_RECYCLE = 128
-RECYCLE_BYTES = 8 << 30       # cap on the memory of the recycled basis (2 * vectors * N doubles)
+RECYCLE_BYTES = 8 << 30       # cap on the memory of the recycled basis (vectors * N doubles; ensembles keep two arrays)
 
 
 def recycle_vectors(num_dofs, want=DEFAULT_RECYCLE):
