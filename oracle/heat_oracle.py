@@ -11,6 +11,8 @@ meshes, outputs, golden vectors or asserting tests for this path (SURVEY.md sect
 oracle therefore restates the published algorithms and is anchored on (i) the reference's
 call sites cited below, (ii) exact polynomial integrals / known-answer element matrices,
 (iii) an independent quadrature implementation of the same forms (tests/test_oracle.py).
+tools/make_reference_goldens.py is the committed recipe that pins it on a machine where the reference's stack runs
+(tests/test_reference_goldens.py consumes its tests/golden/ref_*.npz files; none exists yet).
 
 What is restated (reference file:line):
   * forms                run_with_diamond.py:321-337, space/space_and_forms.py:98-117
