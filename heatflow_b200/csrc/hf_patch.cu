@@ -626,7 +626,7 @@ static const int kPatchRpt[6] = {4, 6, 8, 10, 12, 14};
 static const int kPatchK[2][6] = {{8, 6, 4, 4, 3, 2}, {2, 1, 0, 0, 0, 0}};   // [share - 1][rows-per-thread index]
 // the pipelined variant keeps six vectors of the own rows in registers, so it caches fewer operator entries (-1: no such
 // kernel); the shared-memory operator part is sized for the smaller of the two caches
-static const int kPipeK[2][6] = {{8, -1, -1, -1, -1, -1}, {-1, -1, -1, -1, -1, -1}};
+static const int kPipeK[2][6] = {{8, 4, -1, -1, -1, -1}, {-1, -1, -1, -1, -1, -1}};
 
 static const void* patch_kernel(int rpt, int share) {
   if (share == 2) {
@@ -655,7 +655,8 @@ static const void* pipe_kernel(int rpt, int share) {
   // 28.7 simulations/s with k_pcg_pipe<4, 1, 2> against 32.4 with the classic k_pcg_patch<4, 2, 2> (two host threads)
   if (share == 2) return nullptr;
   switch (rpt) {
-    case 4: return (const void*)k_pcg_pipe<4, 8, 1>;       // rpt 6 (K = 4) measured 2 % slower than the classic kernel
+    case 4: return (const void*)k_pcg_pipe<4, 8, 1>;
+    case 6: return (const void*)k_pcg_pipe<6, 4, 1>;       // meshes of 1.5e5 - 2.3e5 dofs (the reference's own gmsh meshes start there)
     default: return nullptr;
   }
 }
