@@ -198,8 +198,9 @@ extern "C" int hf_set_mesh(hf_ctx* c, int32_t N, int32_t E, int32_t nv, const do
     // into the other three: a warp publishes its boundary packets after a quarter of its SpMV and computes the interior
     // rows while they travel through L2, instead of publishing at the end and waiting a full trip for the neighbours'.
     // The patches themselves (sets of rows, halo lists) do not change; inside a class the Hilbert order is kept.
-    // (the same for 1536-row patches, six slices per warp, on meshes of up to one such patch per SM)
-    const int spw_bf = ((int64_t)N + 1023) / 1024 <= c->sm_count ? 4 : (((int64_t)N + 1535) / 1536 <= c->sm_count ? 6 : 0);
+    // (the same for 1536- and 2048-row patches, six / eight slices per warp, on meshes of up to one such patch per SM)
+    const int spw_bf = ((int64_t)N + 1023) / 1024 <= c->sm_count ? 4 : ((int64_t)N + 1535) / 1536 <= c->sm_count ? 6
+                       : ((int64_t)N + 2047) / 2048 <= c->sm_count ? 8 : 0;
     if (nv == 3 && !getenv("HF_NO_BOUNDARY_FIRST") && spw_bf) {
       const int SPW = spw_bf, PB = 256 * spw_bf;               // slices per warp, rows per patch
       std::vector<unsigned char> bnd(N, 0);

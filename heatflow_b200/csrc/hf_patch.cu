@@ -626,7 +626,7 @@ static const int kPatchRpt[6] = {4, 6, 8, 10, 12, 14};
 static const int kPatchK[2][6] = {{8, 6, 4, 4, 3, 2}, {2, 1, 0, 0, 0, 0}};   // [share - 1][rows-per-thread index]
 // the pipelined variant keeps six vectors of the own rows in registers, so it caches fewer operator entries (-1: no such
 // kernel); the shared-memory operator part is sized for the smaller of the two caches
-static const int kPipeK[2][6] = {{8, 4, -1, -1, -1, -1}, {-1, -1, -1, -1, -1, -1}};
+static const int kPipeK[2][6] = {{8, 4, 2, -1, -1, -1}, {-1, -1, -1, -1, -1, -1}};
 
 static const void* patch_kernel(int rpt, int share) {
   if (share == 2) {
@@ -657,6 +657,7 @@ static const void* pipe_kernel(int rpt, int share) {
   switch (rpt) {
     case 4: return (const void*)k_pcg_pipe<4, 8, 1>;
     case 6: return (const void*)k_pcg_pipe<6, 4, 1>;       // meshes of 1.5e5 - 2.3e5 dofs (the reference's own gmsh meshes start there)
+    case 8: return (const void*)k_pcg_pipe<8, 2, 1>;       // up to 3.0e5 dofs
     default: return nullptr;
   }
 }
