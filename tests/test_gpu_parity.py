@@ -296,12 +296,13 @@ def test_recycle_single_steps_and_argument_errors(small_nd):
     s2.close()
 
 
-def test_mid_size_mesh_runs_on_chip_with_the_patch_kernel():
-    # 2.2e5 dofs (the size of the reference's own gmsh meshes): too large for the contiguous-range kernel,
-    # auto mode picks the Hilbert order and the patch kernel; runner defaults (warm start + recycled guess)
-    c = build_case("geballe_with_diamond", 0.8)
+@pytest.mark.parametrize("scale", [0.8, 0.7], ids=["2.2e5-dofs-1536-row-patches", "2.8e5-dofs-2048-row-patches"])
+def test_mid_size_mesh_runs_on_chip_with_the_patch_kernel(scale):
+    # 2.2e5 / 2.8e5 dofs (the size of the reference's own gmsh meshes): more than 1024 rows per SM, auto mode picks the
+    # pipelined on-chip kernel with 6 / 8 rows per thread; runner defaults (warm start + recycled guess)
+    c = build_case("geballe_with_diamond", scale)
     s = make_solver(c, warm=1.0, recycle=32)
-    assert s.on_chip()
+    assert s.solver_path() == 4                        # pipelined on-chip kernel
     O = make_oracle(c)
     watch = ho.nearest_nodes(c.nodes, [(c.heating_z + 0.5 * 6.2e-8, 0.0), (0.951e-6, 0.0), (0.0, 5e-6)])
     S = 16
