@@ -22,6 +22,7 @@ Extra objects on the JSON line:
                 ``roofline_1m_launch_per_iteration``: the same with ``k_pcg_iter`` (round-1 scheme).
   roofline_4m   the same on a 4.3 M-dof refinement: 580 MB per iteration, far beyond the L2.
   roofline_ens_1m  ``k_ens_iter`` (batched multi-RHS ensemble, 16 sweep variants per tile) on the same >= 1 M-dof mesh.
+  mid_mesh / mid_mesh_220k  the headline cfg refined to 3.8e5 / 2.2e5 dofs (the sizes of the reference's own gmsh meshes).
   sweep         BASELINE config #5 through ``run_parameter_sweep``: 128 variants per GPU, run folders written;
                 ``config.sweep_sims_per_s`` / ``config.sweep_cpu_sims_per_s`` repeat the two numbers.
   cpu_baseline  the scipy sparse-LU oracle on this host (1 core), same steps; ``parity_check`` compares the GPU
@@ -550,6 +551,7 @@ def run_ours(args, rank, world, local_rank):
                                                  traffic=traffic.get("k_pcg_stream_4m"))
         # the size of the reference's own gmsh meshes (2.1e5 - 4.3e5 nodes): still on chip
         line["mid_mesh"] = large_mesh_run(build_case(WORKLOAD, 0.6), local_rank, args.rtol, args.warm_start, args.recycle)
+        line["mid_mesh_220k"] = large_mesh_run(build_case(WORKLOAD, 0.8), local_rank, args.rtol, args.warm_start, args.recycle)
     # CPU baseline on this host (bounded sample) and the parity check against it: the oracle runs the same steps
     if not args.skip_cpu:
         t_loop, t_asm, t_fac, O, ohist = oracle_loop(c, steps, W, watch)
